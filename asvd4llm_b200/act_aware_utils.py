@@ -1,0 +1,54 @@
+"""calib_input_distribution — upstream act_aware_utils.py:47-95 with the hook arithmetic (:64-74) in the
+asvd_absstat_accum kernel.  Cache file name and format are upstream's:
+cache/{model_id with / -> _}_calib_input_distribution_{method}.pt = {module name: Tensor[in_features]}."""
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+def _cache_file(model, method):
+    model_id = model.config._name_or_path
+    return f"cache/{model_id.replace('/', '_')}_calib_input_distribution_{method}.pt"
+
+
+@torch.no_grad()
+def calib_input_distribution(model, calib_loader, method, use_cache=True):
+    cache_file = _cache_file(model, method)
+    if os.path.exists(cache_file) and use_cache:
+        table = torch.load(cache_file, map_location="cpu")
+        for name, module in model.named_modules():
+            if isinstance(module, nn.Linear):
+                module.scaling_diag_matrix = table[name].to(module.weight.device)
+        return
+    model.eval()
+
+    def hook(module, inp, out):
+        x = inp[0].detach()
+        if x.dim() > 2 and x.numel() // (x.shape[-1] * x.shape[-2]) != 1:
+            # upstream's `.view(-1)` (:66) is only meaningful for batch 1
+            raise ValueError("calib_input_distribution expects batch-1 activations, got " + str(tuple(x.shape)))
+        acc = module.scaling_diag_matrix
+        if not torch.is_tensor(acc):                           # python int 0 until the first call (:80)
+            acc = torch.zeros(x.shape[-1], dtype=x.dtype, device=x.device)
+            module.scaling_diag_matrix = acc
+        if "abs_mean" in method or "abs_max" in method:
+            _lib.absstat_accum(x, acc, method)
+
+    handles = []
+    for _, module in model.named_modules():
+        if isinstance(module, nn.Linear):
+            module.scaling_diag_matrix = 0
+            handles.append(module.register_forward_hook(hook))
+    device = getattr(model, "device", None) or next(model.parameters()).device
+    for batch in calib_loader:
+        batch = {k: v.to(device) for k, v in batch.items()}
+        model(**batch)
+    table = {}
+    for name, module in model.named_modules():
+        if isinstance(module, nn.Linear):
+            module._forward_hooks.clear()                      # upstream clears every hook (:93)
+            table[name] = module.scaling_diag_matrix
+    torch.save(table, cache_file)

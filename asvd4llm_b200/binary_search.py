@@ -1,0 +1,118 @@
+"""binary_search_truncation_rank — upstream binary_search.py:10-131: global rank allocation over the
+(layer, ratio, ppl) list and the final decomposition of every selected layer.  Quirks kept on purpose
+(SURVEY.md §9): ratio >= 1 entries dropped outside kv mode, kv mode halves the ratio, the final allocation
+uses the LAST `mid` of the loop, log lines are upstream's."""
+import time
+from collections import defaultdict
+
+import torch
+import torch.nn as nn
+
+from .evaluate_utils import evaluate_perplexity
+from .modules.svd_linear import SVDLinear, from_linear_batch, clear_cache
+from .sensitivity import enumerate_linears
+
+
+def _ratios_after_cut(sorted_list, cut, layer_names, default_ratio):
+    chosen = {name: default_ratio for name in layer_names}
+    for layer, ratio, _ in sorted_list[cut:]:
+        chosen[layer] = min(chosen[layer], ratio)
+    return chosen
+
+
+def search_allocation(model, sensitivity_dict, calib_loader, args):
+    """The search part (binary_search.py:29-110).  Returns ({layer: ratio}, default_ratio)."""
+    by_name = dict(model.named_modules())
+    where = {lin: (father, name) for father, name, _, lin in enumerate_linears(model)}
+    if args.compress_kv_cache:
+        ratio_target = args.kv_cache_ratio_target
+        sensitivity_dict = {k: v for k, v in sensitivity_dict.items() if "k_proj" in k or "v_proj" in k}
+        assert args.ppl_target < 0, "ppl_target is not supported when compressing kv_cache"
+        default_ratio = 2
+    else:
+        ratio_target = args.param_ratio_target
+        default_ratio = 1
+    print(f"=== {'compress kv_cache' if args.compress_kv_cache else 'compress weight'} target: "
+          f"ppl={args.ppl_target}, ratio_target={ratio_target} ===")
+    flat = []
+    for layer, table in sensitivity_dict.items():
+        for ratio, ppl in table.items():
+            if not args.compress_kv_cache and ratio >= 1:
+                continue
+            flat.append((layer, ratio, ppl))
+    flat = sorted(flat, key=lambda t: -t[2])
+    low, high, mid = 0, len(flat) - 1, None
+    assert args.ppl_target > 0 or ratio_target > 0
+    input_ids = torch.cat([b["input_ids"] for b in calib_loader], 0)
+    while low < high:
+        mid = (low + high) // 2
+        chosen = _ratios_after_cut(flat, mid, sensitivity_dict.keys(), default_ratio)
+        tot = comp = 0
+        if args.ppl_target > 0:
+            assert not args.compress_kv_cache, "ppl_target is not supported when compressing kv_cache now"
+            for layer, ratio in chosen.items():
+                raw = by_name[layer]
+                father, name = where[raw]
+                setattr(father, name, SVDLinear.from_linear(raw, param_ratio=ratio, alpha=args.alpha,
+                                                            act_aware=args.act_aware, sigma_fuse=args.sigma_fuse,
+                                                            rank_align=args.rank_align))
+                tot += raw.weight.numel()
+                comp += raw.weight.numel() * ratio
+            ppl = evaluate_perplexity(model, input_ids, args.n_calib_samples)
+            print(f"low={low} mid={mid}, high={high}, ppl={ppl}, param_ratio={comp / tot}")
+            if ppl < args.ppl_target:
+                high = mid
+            else:
+                low = mid + 1
+        else:
+            for layer, ratio in chosen.items():
+                numel = by_name[layer].weight.numel()
+                tot += numel
+                comp += numel * ratio
+            now_ratio = comp / tot
+            if args.compress_kv_cache:
+                now_ratio /= 2          # param ratio counts ALinear + BLinear; the rank ratio is half of it
+            print(f"low={low} mid={mid}, high={high}, now_ratio={now_ratio}, params=({comp}/{tot})")
+            if now_ratio > ratio_target:
+                high = mid
+            else:
+                low = mid + 1
+    print("=== Searching done, decomposing layers... ===")
+    return _ratios_after_cut(flat, mid, sensitivity_dict.keys(), default_ratio), default_ratio   # stale mid (:106)
+
+
+def decompose_layers(model, chosen, default_ratio, args, layer_filter=None, batch_limit_bytes=8 << 30):
+    """The final pass (binary_search.py:112-128), batching same-shape layers per kernel call.
+    Returns the number of layers replaced."""
+    by_name = dict(model.named_modules())
+    where = {lin: (father, name) for father, name, _, lin in enumerate_linears(model)}
+    groups = defaultdict(list)
+    for layer, ratio in chosen.items():
+        if ratio == default_ratio or (layer_filter is not None and not layer_filter(layer)):
+            continue
+        raw = by_name[layer]
+        groups[(tuple(raw.weight.shape), raw.weight.dtype, raw.weight.device)].append((layer, ratio, raw))
+    done = 0
+    for (shape, _, _), items in groups.items():
+        m, n = shape
+        per = 4 * min(m, n) * (m + n + min(m, n)) + 1
+        step = max(1, min(8, batch_limit_bytes // per))
+        for i in range(0, len(items), step):
+            part = items[i:i + step]
+            mods = from_linear_batch([raw for _, _, raw in part], [ratio for _, ratio, _ in part], alpha=args.alpha,
+                                     act_aware=args.act_aware, sigma_fuse=args.sigma_fuse, rank_align=args.rank_align)
+            for (layer, _, raw), mod in zip(part, mods):
+                raw.to("cpu")                                   # upstream frees the replaced weight (:127)
+                father, name = where[raw]
+                setattr(father, name, mod)
+                done += 1
+    clear_cache()
+    return done
+
+
+def binary_search_truncation_rank(model, sensitivity_dict, calib_loader, args):
+    chosen, default_ratio = search_allocation(model, sensitivity_dict, calib_loader, args)
+    st = time.time()
+    decompose_layers(model, chosen, default_ratio, args)
+    ed = time.time()
+    print(f"decompose time: {ed - st}")

@@ -1,0 +1,194 @@
+// a1 (calibration statistic), a3 (scaling vector) and the first-round body of a7 (low-rank forward).
+#include <float.h>
+#include "common.cuh"
+#include "gemm_simt.cuh"
+
+namespace asvd {
+
+// ------------------------------------------------------------------------------------------------ a3
+// modules/svd_linear.py:48-59.  Every intermediate is rounded to the statistics' dtype T, as the upstream
+// tensor expressions `1 * sdm**alpha`, `*= fisher**alpha`, `+= 1e-6` do.
+template <typename T>
+__device__ __forceinline__ float pow_rounded(float x, float alpha) {
+  float v = (alpha == 0.5f) ? sqrtf(x) : (alpha == 1.f ? x : (alpha == 2.f ? x * x : powf(x, alpha)));
+  return to_f32<T>(from_f32<T>(v));
+}
+
+template <typename T>
+__global__ void scaling_vector_kernel(const T* __restrict__ sdm, const T* __restrict__ fisher, int n, float alpha,
+                                      float* __restrict__ out) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float v = 1.f;
+  bool any = false;
+  if (sdm) { v = pow_rounded<T>(to_f32<T>(sdm[j]), alpha); any = true; }
+  if (fisher) {
+    float f = pow_rounded<T>(to_f32<T>(fisher[j]), alpha);
+    v = any ? to_f32<T>(from_f32<T>(v * f)) : f;
+    any = true;
+  }
+  // python: `scaling_diag_matrix += 1e-6` on a tensor of dtype T (a python float when no statistic exists)
+  v = any ? to_f32<T>(from_f32<T>(v + 1e-6f)) : (float)(1.0 + 1e-6);
+  out[j] = v;
+}
+
+// ------------------------------------------------------------------------------------------------ a1
+// act_aware_utils.py:64-74.  Stage 1: per-column partial sum / max of |x| over a slab of rows.
+constexpr int STAT_SPLITS = 32;
+
+template <typename T>
+__global__ void __launch_bounds__(256) absstat_partial_kernel(const T* __restrict__ x, int64_t ldx, int64_t L, int n,
+                                                              int mode, float* __restrict__ partial) {
+  // 256 threads = 64 column lanes x 4 row lanes; each column lane owns 2 adjacent columns
+  __shared__ float red[4][128];
+  const int cl = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  const int j = blockIdx.x * 128 + cl * 2;
+  const int64_t rows_per = (L + STAT_SPLITS - 1) / STAT_SPLITS;
+  const int64_t i0 = blockIdx.y * rows_per, i1 = min(L, i0 + rows_per);
+  float a0 = 0.f, a1 = 0.f;
+  const bool ok0 = j < n, ok1 = j + 1 < n;
+  const bool vec = ok1 && ((ldx & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & (2 * sizeof(T) - 1)) == 0);
+  for (int64_t i = i0 + rl; i < i1; i += 4) {
+    float v0 = 0.f, v1 = 0.f;
+    const T* p = x + i * ldx + j;
+    if (vec) {
+      if constexpr (sizeof(T) == 2) {
+        unsigned raw = *reinterpret_cast<const unsigned*>(p);
+        const T* h = reinterpret_cast<const T*>(&raw);
+        v0 = fabsf(to_f32<T>(h[0])); v1 = fabsf(to_f32<T>(h[1]));
+      } else {
+        float2 f = *reinterpret_cast<const float2*>(p);
+        v0 = fabsf(f.x); v1 = fabsf(f.y);
+      }
+    } else {
+      if (ok0) v0 = fabsf(to_f32<T>(p[0]));
+      if (ok1) v1 = fabsf(to_f32<T>(p[1]));
+    }
+    if (mode == ASVD_STAT_ABS_MEAN) { a0 += v0; a1 += v1; }
+    else {
+      // NaN-propagating max, like torch.amax
+      a0 = (v0 != v0 || a0 != a0) ? NAN : fmaxf(a0, v0);
+      a1 = (v1 != v1 || a1 != a1) ? NAN : fmaxf(a1, v1);
+    }
+  }
+  red[rl][cl * 2] = a0; red[rl][cl * 2 + 1] = a1;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int c = threadIdx.x;
+    float v = red[0][c];
+    for (int r = 1; r < 4; ++r) {
+      float w = red[r][c];
+      if (mode == ASVD_STAT_ABS_MEAN) v += w;
+      else v = (v != v || w != w) ? NAN : fmaxf(v, w);
+    }
+    const int col = blockIdx.x * 128 + c;
+    if (col < n) partial[(int64_t)blockIdx.y * n + col] = v;
+  }
+}
+
+template <typename T>
+__global__ void absstat_combine_kernel(const float* __restrict__ partial, int n, int64_t L, int mode, T* __restrict__ acc) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float v = partial[j];
+  for (int s = 1; s < STAT_SPLITS; ++s) {
+    float w = partial[(int64_t)s * n + j];
+    if (mode == ASVD_STAT_ABS_MEAN) v += w;
+    else v = (v != v || w != w) ? NAN : fmaxf(v, w);
+  }
+  float old = to_f32<T>(acc[j]);
+  if (mode == ASVD_STAT_ABS_MEAN) {
+    float mean = to_f32<T>(from_f32<T>(v / (float)L));     // abs().mean(dim=-2) in the activation dtype
+    acc[j] = from_f32<T>(old + mean);                      // scaling_diag_matrix += abs_mean
+  } else {
+    float cur = to_f32<T>(from_f32<T>(v));
+    acc[j] = from_f32<T>(cur > old ? cur : old);           // torch.where(abs_max > acc, abs_max, acc)
+  }
+}
+
+}  // namespace asvd
+
+using namespace asvd;
+
+template <typename T>
+static int absstat_run(const void* x, int64_t ldx, int64_t L, int n, int mode, void* acc, float* partial, cudaStream_t st) {
+  dim3 grid((n + 127) / 128, STAT_SPLITS);
+  absstat_partial_kernel<T><<<grid, 256, 0, st>>>((const T*)x, ldx, L, n, mode, partial);
+  absstat_combine_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(partial, n, L, mode, (T*)acc);
+  ASVD_CUDA_CHECK(cudaGetLastError());
+  return ASVD_OK;
+}
+
+template <typename T>
+static int forward_run(const void* x, int64_t ldx, int64_t M, int n, const void* B, int64_t ldb, int r, const void* A,
+                       int64_t lda, int m, const void* bias, void* y, int64_t ldy, void* scratch, cudaStream_t st) {
+  GemmBatch gb;
+  memset(&gb, 0, sizeof(gb));
+  T* t = reinterpret_cast<T*>(scratch);
+  // t[M, r] = x B^T  (materialised in the module dtype, as upstream's BLinear output is)
+  cudaError_t e = launch_gemm128<T, T, T, false>((const T*)x, ldx, (const T*)B, ldb, t, r, (int)M, r, n, nullptr, nullptr,
+                                                 (const T*)nullptr, 1, gb, st);
+  ASVD_CUDA_CHECK(e);
+  // y[M, m] = t A^T + bias
+  e = launch_gemm128<T, T, T, false>(t, r, (const T*)A, lda, (T*)y, ldy, (int)M, m, r, nullptr, nullptr, (const T*)bias, 1, gb, st);
+  ASVD_CUDA_CHECK(e);
+  return ASVD_OK;
+}
+
+extern "C" {
+
+int asvd_scaling_vector(const void* sdm, const void* fisher, int stat_dtype, int n, double alpha, float* scale_out,
+                        void* stream) {
+  ASVD_REQUIRE(scale_out && n > 0, "bad argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid((n + 255) / 256);
+  switch (stat_dtype) {
+    case ASVD_F32: scaling_vector_kernel<float><<<grid, 256, 0, st>>>((const float*)sdm, (const float*)fisher, n, (float)alpha, scale_out); break;
+    case ASVD_F16: scaling_vector_kernel<__half><<<grid, 256, 0, st>>>((const __half*)sdm, (const __half*)fisher, n, (float)alpha, scale_out); break;
+    case ASVD_BF16: scaling_vector_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)sdm, (const __nv_bfloat16*)fisher, n, (float)alpha, scale_out); break;
+    default: set_error("bad dtype %d", stat_dtype); return ASVD_ERR_INVALID;
+  }
+  ASVD_CUDA_CHECK(cudaGetLastError());
+  return ASVD_OK;
+}
+
+size_t asvd_absstat_scratch_bytes(int n) { return n > 0 ? sizeof(float) * (size_t)STAT_SPLITS * n : 0; }
+
+
+int asvd_absstat_accum(const void* x, int64_t ldx, int64_t L, int n, int dtype, int mode, void* acc, void* scratch,
+                       size_t scratch_bytes, void* stream) {
+  ASVD_REQUIRE(x && acc && scratch && L > 0 && n > 0 && ldx >= n, "bad argument");
+  ASVD_REQUIRE(mode == ASVD_STAT_ABS_MEAN || mode == ASVD_STAT_ABS_MAX, "bad mode %d", mode);
+  if (scratch_bytes < asvd_absstat_scratch_bytes(n)) { set_error("scratch too small"); return ASVD_ERR_WORKSPACE; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* partial = reinterpret_cast<float*>(scratch);
+  switch (dtype) {
+    case ASVD_F32: return absstat_run<float>(x, ldx, L, n, mode, acc, partial, st);
+    case ASVD_F16: return absstat_run<__half>(x, ldx, L, n, mode, acc, partial, st);
+    case ASVD_BF16: return absstat_run<__nv_bfloat16>(x, ldx, L, n, mode, acc, partial, st);
+  }
+  set_error("bad dtype %d", dtype);
+  return ASVD_ERR_INVALID;
+}
+
+size_t asvd_lowrank_forward_scratch_bytes(int64_t M, int r) { return (M > 0 && r > 0) ? (size_t)M * r * 4 : 0; }
+
+
+int asvd_lowrank_forward(const void* x, int64_t ldx, int64_t M, int n, const void* B, int64_t ldb, int r, const void* A,
+                         int64_t lda, int m, const void* bias, void* y, int64_t ldy, int dtype, void* scratch,
+                         size_t scratch_bytes, void* stream) {
+  ASVD_REQUIRE(x && B && A && y && scratch, "null pointer");
+  ASVD_REQUIRE(M > 0 && M < (1ll << 31) && n > 0 && r > 0 && m > 0, "bad shape");
+  ASVD_REQUIRE(ldx >= n && ldb >= n && lda >= r && ldy >= m, "bad leading dimension");
+  if (scratch_bytes < asvd_lowrank_forward_scratch_bytes(M, r)) { set_error("scratch too small"); return ASVD_ERR_WORKSPACE; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (dtype) {
+    case ASVD_F16: return forward_run<__half>(x, ldx, M, n, B, ldb, r, A, lda, m, bias, y, ldy, scratch, st);
+    case ASVD_BF16: return forward_run<__nv_bfloat16>(x, ldx, M, n, B, ldb, r, A, lda, m, bias, y, ldy, scratch, st);
+    case ASVD_F32: return forward_run<float>(x, ldx, M, n, B, ldb, r, A, lda, m, bias, y, ldy, scratch, st);
+  }
+  set_error("bad dtype %d", dtype);
+  return ASVD_ERR_INVALID;
+}
+
+}  // extern "C"

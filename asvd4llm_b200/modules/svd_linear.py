@@ -1,0 +1,168 @@
+"""SVDLinear — drop-in for upstream modules/svd_linear.py:7-109, computed by the sm_100a kernels.
+
+Same names, arguments and failure behaviour as upstream:
+  * SVDLinear(U, S, V, bias=None, sigma_fuse="UV")             (svd_linear.py:8-24)
+  * SVDLinear.from_linear(linear, param_ratio, act_aware=False, ic_split=1, oc_split=1, alpha=1,
+                          sigma_fuse="UV", rank_align=1)       (svd_linear.py:26-103)
+  * forward(inp) = ALinear(BLinear(inp))                       (svd_linear.py:105-109)
+  * children `ALinear` [m, r] (+bias) and `BLinear` [r, n]; attribute `truncation_rank`.
+
+Differences, all deliberate (DESIGN.md §"Deviations"):
+  * the factorisation is an EXACT SVD of fp32(W)*diag(s) (one-sided block Jacobi on the GPU), not
+    torch.svd_lowrank — BASELINE.json's north_star grades against torch.linalg.svd;
+  * one SVD per (linear, scaling) is cached, so the six ratios of the sensitivity sweep re-slice it;
+  * there is no CPU compute path: weights living on the CPU are staged through the current CUDA device.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+
+
+class SVDLinear(nn.Module):
+    def __init__(self, U, S, V, bias=None, sigma_fuse="UV") -> None:
+        super().__init__()
+        self.ALinear = nn.Linear(U.size(1), U.size(0), bias=bias is not None)
+        if bias is not None:
+            self.ALinear.bias.data = bias                       # shared storage, as upstream (:12-13)
+        self.BLinear = nn.Linear(V.size(1), V.size(0), bias=False)
+        self.truncation_rank = S.size(0)
+        if sigma_fuse == "UV":
+            root = S.sqrt()
+            self.ALinear.weight.data = (U * root).contiguous()
+            self.BLinear.weight.data = (V.t() * root.view(-1, 1)).contiguous()
+        elif sigma_fuse == "U":
+            self.ALinear.weight.data = (U * S).contiguous()
+            self.BLinear.weight.data = V.t().contiguous()
+        elif sigma_fuse == "V":
+            self.ALinear.weight.data = U.contiguous()
+            self.BLinear.weight.data = (V.t() * S.view(-1, 1)).contiguous()
+
+    # ------------------------------------------------------------------ construction from kernel outputs
+    @classmethod
+    def _from_factors(cls, A: torch.Tensor, B: torch.Tensor, bias: Optional[torch.Tensor]) -> "SVDLinear":
+        self = cls.__new__(cls)
+        nn.Module.__init__(self)
+        m, r = A.shape
+        n = B.shape[1]
+        with torch.device("meta"):
+            a = nn.Linear(r, m, bias=bias is not None)
+            b = nn.Linear(n, r, bias=False)
+        a.weight = nn.Parameter(A)
+        if bias is not None:
+            a.bias = nn.Parameter(bias)                         # same storage as the original bias (:12-13)
+        b.weight = nn.Parameter(B)
+        self.ALinear, self.BLinear = a, b                       # registration order as upstream (:10,14)
+        self.truncation_rank = r
+        return self
+
+    @staticmethod
+    def from_linear(linear: nn.Linear, param_ratio: float, act_aware=False, ic_split=1, oc_split=1, alpha=1,
+                    sigma_fuse="UV", rank_align=1):
+        return from_linear_batch([linear], [param_ratio], act_aware=act_aware, ic_split=ic_split, oc_split=oc_split,
+                                 alpha=alpha, sigma_fuse=sigma_fuse, rank_align=rank_align)[0]
+
+    def forward(self, inp):
+        # y = (x B^T) A^T + b in one C-ABI call (asvd_lowrank_forward)
+        return _lib.lowrank_forward(inp, self.ALinear.weight, self.BLinear.weight, self.ALinear.bias)
+
+
+# ---------------------------------------------------------------------------------------------------------
+_CACHE = {"key": None, "fact": None, "index": None}      # single entry: the sweep visits one layer at a time
+
+
+def clear_cache():
+    _CACHE.update(key=None, fact=None, index=None)
+
+
+def _stat(linear, name):
+    t = getattr(linear, name, None)
+    return t if torch.is_tensor(t) else None
+
+
+def _key(linear, act_aware, alpha):
+    def sig(t):
+        return None if t is None else (t.data_ptr(), t._version, tuple(t.shape), t.dtype)
+    w = linear.weight
+    return (id(linear), sig(w.data), bool(act_aware), float(alpha) if act_aware else None,
+            sig(_stat(linear, "scaling_diag_matrix")) if act_aware else None,
+            sig(_stat(linear, "fisher_info")) if act_aware else None)
+
+
+def _compute_device(t: torch.Tensor) -> torch.device:
+    if t.is_cuda:
+        return t.device
+    if not torch.cuda.is_available():
+        raise RuntimeError("asvd4llm_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _fallback(linear: nn.Linear):
+    # upstream svd_linear.py:66-68,80-98: a fresh nn.Linear (random init, with bias) in the weight dtype/device.
+    # ASVD_B200_KEEP_RAW_ON_FAILURE=1 keeps the original layer instead (recommended).
+    if os.environ.get("ASVD_B200_KEEP_RAW_ON_FAILURE", "0") == "1":
+        return linear
+    return nn.Linear(linear.in_features, linear.out_features).to(linear.weight.dtype).to(linear.weight.device)
+
+
+def factorise(linears: Sequence[nn.Linear], act_aware: bool, alpha: float, tol: float = 0.0, max_sweeps: int = 0):
+    """One batched asvd_scaled_svd call over same-shape linears.  Returns (_lib.Factorisation | None, dev)."""
+    w0 = linears[0].weight.data
+    dev = _compute_device(w0)
+    weights, scales = [], []
+    for lin in linears:
+        w = lin.weight.data
+        weights.append(w.to(dev, non_blocking=True))
+        if act_aware:
+            sdm, fisher = _stat(lin, "scaling_diag_matrix"), _stat(lin, "fisher_info")
+            if sdm is None and fisher is None:
+                # upstream: `scaling_diag_matrix = 1; ... += 1e-6` then `.view` on a python float (:48-60)
+                raise AttributeError("'float' object has no attribute 'view'")
+            scales.append(_lib.scaling_vector(sdm, fisher, alpha, lin.in_features, dev))
+        else:
+            scales.append(None)
+    try:
+        return _lib.scaled_svd(weights, scales, tol=tol, max_sweeps=max_sweeps), dev
+    except _lib.AsvdError as e:
+        if e.status == _lib.ERR_NONFINITE:
+            return None, dev
+        raise
+
+
+def from_linear_batch(linears: Sequence[nn.Linear], param_ratios: Sequence[float], act_aware=False, ic_split=1,
+                      oc_split=1, alpha=1, sigma_fuse="UV", rank_align=1) -> List[nn.Module]:
+    """from_linear for several SAME-SHAPE linears in one kernel batch (fills the GPU when one matrix's
+    block pairs do not).  Semantics per layer are exactly SVDLinear.from_linear."""
+    assert ic_split == 1 or oc_split == 1
+    assert len(linears) == len(param_ratios) and len(linears) > 0
+    m, n = linears[0].out_features, linears[0].in_features
+    ranks = [min(_lib.rank_for_ratio(m, n, pr, rank_align), min(m, n)) for pr in param_ratios]
+    if min(ranks) <= 0:
+        raise ValueError(f"param_ratio too small for a {m}x{n} layer: rank {min(ranks)}")
+    fact = None
+    if len(linears) == 1:
+        key = _key(linears[0], act_aware, alpha)
+        if _CACHE["key"] == key:
+            fact, dev = _CACHE["fact"], _CACHE["fact"].workspace.device if _CACHE["fact"] is not None else None
+    if fact is None:
+        fact, dev = factorise(linears, act_aware, alpha)
+        if len(linears) == 1:
+            _CACHE.update(key=_key(linears[0], act_aware, alpha), fact=fact)
+    out = []
+    for b, (lin, r) in enumerate(zip(linears, ranks)):
+        if fact is None:
+            print("nan in S")                                    # upstream message (:82)
+            out.append(_fallback(lin))
+            continue
+        w = lin.weight.data
+        A, B = fact.extract(r, sigma_fuse, w.dtype, b)
+        if A.device != w.device:
+            A, B = A.to(w.device), B.to(w.device)
+        bias = lin.bias.data if lin.bias is not None else None
+        out.append(SVDLinear._from_factors(A, B, bias))
+    return out

@@ -1,0 +1,63 @@
+"""calib_sensitivity_ppl — upstream sensitivity.py:10-61.  Same table ({layer: {ratio: ppl}}, python floats),
+same sweep order, same cache file; the six factorisations per layer are six slices of ONE SVD."""
+import os
+
+import torch
+import torch.nn as nn
+
+from .evaluate_utils import evaluate_perplexity
+from .modules.svd_linear import SVDLinear, clear_cache
+
+RATIOS = [0.4, 0.5, 0.6, 0.7, 0.8, 0.9]                       # sensitivity.py:39
+KV_RATIOS = [0.1 * i for i in range(1, 20)]                  # sensitivity.py:37 (float keys like 0.30000000000000004)
+
+
+def enumerate_linears(model):
+    """upstream's explicit-stack DFS (sensitivity.py:19-33): last-registered child first, stops at nn.Linear.
+    Yields (father, child name, full name, linear) in sweep order."""
+    full_name = {module: name for name, module in model.named_modules()}
+    found, stack = [], [model]
+    while stack:
+        sub = stack.pop()
+        for name, child in sub.named_children():
+            if isinstance(child, nn.Linear):
+                found.append((sub, name, full_name[child], child))
+            else:
+                stack.append(child)
+    return found
+
+
+def sensitivity_cache_file(model, args):
+    model_id = model.config._name_or_path
+    return (f"cache/{model_id.replace('/', '_')}_sensitivity_{args.scaling_method}_{args.alpha}_"
+            f"{args.n_calib_samples}_{args.calib_dataset}.pt")
+
+
+@torch.no_grad()
+def calib_sensitivity_ppl(model, calib_loader, args, use_cache=True, layer_filter=None):
+    """layer_filter (extension): callable(full_name) -> bool restricting the sweep to a shard of layers; the
+    multi-GPU driver merges the shards (asvd4llm_b200.sharding)."""
+    cache_file = sensitivity_cache_file(model, args)
+    if os.path.exists(cache_file) and use_cache and layer_filter is None:
+        return torch.load(cache_file, map_location="cpu")
+    model.eval()
+    ratios = KV_RATIOS if args.compress_kv_cache else RATIOS
+    input_ids = torch.cat([b["input_ids"] for b in calib_loader], 0)
+    print(f"input_ids.shape={input_ids.shape}")
+    table = {}
+    for father, name, full_name, raw in enumerate_linears(model):
+        if layer_filter is not None and not layer_filter(full_name):
+            continue
+        table[full_name] = {}
+        for ratio in ratios:
+            svd_linear = SVDLinear.from_linear(raw, param_ratio=ratio, alpha=args.alpha, act_aware=True,
+                                               rank_align=args.rank_align)       # act_aware hard-coded (:50)
+            setattr(father, name, svd_linear)
+            ppl = evaluate_perplexity(model, input_ids, args.n_calib_samples)
+            table[full_name][ratio] = ppl
+            print(f"{full_name} {ratio} {ppl}")
+        setattr(father, name, raw)
+    clear_cache()
+    if layer_filter is None:
+        torch.save(table, cache_file)
+    return table

@@ -1,0 +1,104 @@
+/* asvd_b200.h — C ABI of the B200-native ASVD hot path.
+ *
+ * The upstream project (hahnyuan/ASVD4LLM) is pure Python and has no FFI; its boundary for this path is a
+ * Python module contract.  This header is what a binding for that contract calls: plain
+ * pointers and sizes, a cudaStream_t passed as void*, `int` status (0 = ok), no torch types, no exceptions.
+ * All pointers are DEVICE pointers unless the name ends in `_host`.  The caller owns every buffer including
+ * the workspace; the library keeps no global state besides a thread-local error string.
+ *
+ * Each entry point cites the upstream code it replaces (paths relative to the upstream tree).
+ */
+#ifndef ASVD_B200_H
+#define ASVD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASVD_B200_VERSION 100
+
+/* element types of caller tensors */
+enum { ASVD_F32 = 0, ASVD_F16 = 1, ASVD_BF16 = 2 };
+/* sigma_fuse modes — modules/svd_linear.py:16-24 */
+enum { ASVD_FUSE_UV = 0, ASVD_FUSE_U = 1, ASVD_FUSE_V = 2 };
+/* calibration statistic — act_aware_utils.py:64-74 */
+enum { ASVD_STAT_ABS_MEAN = 0, ASVD_STAT_ABS_MAX = 1 };
+/* status codes */
+enum {
+  ASVD_OK = 0,
+  ASVD_ERR_INVALID = 1,      /* bad argument */
+  ASVD_ERR_WORKSPACE = 2,    /* workspace too small */
+  ASVD_ERR_CUDA = 3,         /* a CUDA call failed; see asvd_last_error() */
+  ASVD_ERR_NONFINITE = 4,    /* NaN/Inf in the input or in the factors (upstream: "nan in S/U/V", svd_linear.py:80-98) */
+  ASVD_ERR_NOT_CONVERGED = 5 /* sweep limit hit above tolerance (factors are still written) */
+};
+
+int asvd_version(void);
+/* thread-local description of the last non-zero status */
+const char* asvd_last_error(void);
+
+/* ---- a2: rank formula — modules/svd_linear.py:39-44.  Host arithmetic, here so every binding agrees. */
+int asvd_rank_for_ratio(int64_t out_features, int64_t in_features, double param_ratio, int rank_align);
+
+/* ---- a3: scaling vector — modules/svd_linear.py:48-59.
+ * scale[j] = rnd(rnd(sdm[j]^alpha) * rnd(fisher[j]^alpha)) + 1e-6, every step rounded to `stat_dtype`
+ * exactly as the upstream in-place tensor expressions do; written as fp32.  sdm / fisher may be NULL. */
+int asvd_scaling_vector(const void* sdm, const void* fisher, int stat_dtype, int n, double alpha,
+                        float* scale_out, void* stream);
+
+/* ---- a3+a4: activation-scaled SVD of `batch` same-shape weights — replaces modules/svd_linear.py:47-65
+ * (w.float() * scale, torch.svd_lowrank) with an exact SVD (one-sided block Jacobi) of W*diag(scale).
+ *
+ *   W_host_ptrs[b]     device pointer (16-byte aligned) to weight b, row-major [m, n], leading dimension ldw
+ *   scale_host_ptrs[b] device pointer to fp32 [n] from asvd_scaling_vector, or NULL entry / NULL array for
+ *                      act_aware=False
+ *   workspace          asvd_svd_workspace_bytes(m, n, batch) bytes, 256-byte aligned.  After the call it
+ *                      holds the full factorisation of every weight (all min(m,n) triplets) and is the
+ *                      handle asvd_svd_extract / asvd_svd_sigma read from.
+ *   tol                convergence threshold on max |<x_p,x_q>| / (|x_p||x_q|); <=0 selects the default
+ *   max_sweeps         <=0 selects the default
+ *   sweeps_out_host    optional host int[batch]: sweeps used
+ * Blocks the calling thread until the factorisation is complete on `stream` (it polls a convergence flag
+ * once per sweep). */
+size_t asvd_svd_workspace_bytes(int m, int n, int batch);
+int asvd_scaled_svd(const void* const* W_host_ptrs, int w_dtype, int64_t ldw, int m, int n, int batch,
+                    const float* const* scale_host_ptrs, void* workspace, size_t workspace_bytes,
+                    float tol, int max_sweeps, int* sweeps_out_host, void* stream);
+
+/* all min(m,n) singular values of weight b of a finished workspace, descending, fp32 (device buffer) */
+int asvd_svd_sigma(const void* workspace, int m, int n, int batch, int b, float* sigma_out, void* stream);
+
+/* ---- a5+a6: rank-r truncation, un-scaling, sigma fusion, cast — replaces modules/svd_linear.py:69-70,
+ * 8-24 and :102.  Re-slices a finished workspace, so the six ratios of the sensitivity sweep
+ * (sensitivity.py:39-52) cost one SVD.
+ *   A_out  [m, r] row-major, lda elements  (ALinear.weight)
+ *   B_out  [r, n] row-major, ldb elements  (BLinear.weight)
+ * (m, n, batch) must repeat the values given to asvd_scaled_svd: the workspace layout is a pure function
+ * of them.  r is clamped by the caller to min(m, n) (upstream quirk: a larger request yields min(m,n)). */
+int asvd_svd_extract(const void* workspace, int m, int n, int batch, int b, int r, int sigma_fuse, int out_dtype,
+                     void* A_out, int64_t lda, void* B_out, int64_t ldb, void* stream);
+
+/* ---- a7: SVDLinear.forward — modules/svd_linear.py:105-109 and ASVDLinear.forward
+ * (huggingface_repos/modeling_asvd_llama.py:11-12).  y = (x B^T) A^T + bias.
+ *   x [M, n] ldx;  B [r, n] ldb;  A [m, r] lda;  bias [m] or NULL;  y [M, m] ldy;  all `dtype` (F16 / BF16)
+ *   scratch: asvd_lowrank_forward_scratch_bytes(M, r) bytes for the [M, r] intermediate */
+size_t asvd_lowrank_forward_scratch_bytes(int64_t M, int r);
+int asvd_lowrank_forward(const void* x, int64_t ldx, int64_t M, int n, const void* B, int64_t ldb, int r,
+                         const void* A, int64_t lda, int m, const void* bias, void* y, int64_t ldy, int dtype,
+                         void* scratch, size_t scratch_bytes, void* stream);
+
+/* ---- a1: calibration statistic of one hook call — act_aware_utils.py:64-74.
+ * x [L, n] ldx in `dtype`; acc [n] in the same dtype (upstream accumulates in the activation dtype).
+ *   ABS_MEAN: acc[j] = rnd(acc[j] + rnd(mean_i |x[i,j]|));  ABS_MAX: acc[j] = max(acc[j], max_i |x[i,j]|)
+ * scratch: asvd_absstat_scratch_bytes(n) bytes. */
+size_t asvd_absstat_scratch_bytes(int n);
+int asvd_absstat_accum(const void* x, int64_t ldx, int64_t L, int n, int dtype, int mode, void* acc,
+                       void* scratch, size_t scratch_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASVD_B200_H */
