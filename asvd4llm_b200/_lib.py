@@ -24,7 +24,9 @@ EXPORTS = [
     "asvd_version", "asvd_last_error", "asvd_rank_for_ratio", "asvd_scaling_vector", "asvd_svd_workspace_bytes",
     "asvd_scaled_svd", "asvd_svd_sigma", "asvd_svd_extract", "asvd_lowrank_forward_scratch_bytes",
     "asvd_lowrank_forward", "asvd_absstat_scratch_bytes", "asvd_absstat_accum",
+    "asvd_profile_enable", "asvd_profile_read", "asvd_launch_count",
 ]
+KERNEL_CLASSES = ["prep", "gram", "solve", "update", "finalize", "extract", "forward", "absstat"]
 
 _lock = threading.Lock()
 _lib = None
@@ -72,6 +74,11 @@ def load() -> C.CDLL:
         lib.asvd_absstat_scratch_bytes.argtypes = [i32]
         lib.asvd_absstat_accum.restype = i32
         lib.asvd_absstat_accum.argtypes = [vp, i64, i64, i32, i32, i32, vp, vp, sz, vp]
+        lib.asvd_profile_enable.restype = None
+        lib.asvd_profile_enable.argtypes = [i32]
+        lib.asvd_profile_read.restype = i32
+        lib.asvd_profile_read.argtypes = [C.POINTER(f64), C.POINTER(C.c_uint64)]
+        lib.asvd_launch_count.restype = C.c_uint64
         _lib = lib
         return lib
 
@@ -215,3 +222,19 @@ def absstat_accum(x: torch.Tensor, acc: torch.Tensor, method: str) -> None:
     with torch.cuda.device(x.device):
         _check(lib.asvd_absstat_accum(x2.data_ptr(), x2.stride(0), x2.shape[0], n, dtype_code(x.dtype), mode,
                                       acc.data_ptr(), scratch.data_ptr(), nbytes, _stream()))
+
+
+def launch_count() -> int:
+    return int(load().asvd_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    load().asvd_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """{class: (total ms, launches since load)} — ms is only accumulated while profiling is enabled."""
+    ms = (C.c_double * 8)()
+    ln = (C.c_uint64 * 8)()
+    load().asvd_profile_read(ms, ln)
+    return {k: (ms[i], int(ln[i])) for i, k in enumerate(KERNEL_CLASSES)}

@@ -29,6 +29,18 @@ void set_error(const char* fmt, ...);
     }                                  \
   } while (0)
 
+// kernel classes for launch counting / optional per-class CUDA-event timing (asvd_profile_*)
+enum Kind { K_PREP = 0, K_GRAM, K_SOLVE, K_UPDATE, K_FINAL, K_EXTRACT, K_FORWARD, K_STAT, K_COUNT };
+void prof_begin(int kind, cudaStream_t st);
+void prof_end(int kind, cudaStream_t st);
+void prof_collect();
+#define ASVD_LAUNCH(kind, st, ...) \
+  do {                             \
+    asvd::prof_begin(kind, st);    \
+    __VA_ARGS__;                   \
+    asvd::prof_end(kind, st);      \
+  } while (0)
+
 static inline int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 static inline size_t dtype_size(int dt) { return dt == ASVD_F32 ? 4 : 2; }
 

@@ -113,8 +113,8 @@ using namespace asvd;
 template <typename T>
 static int absstat_run(const void* x, int64_t ldx, int64_t L, int n, int mode, void* acc, float* partial, cudaStream_t st) {
   dim3 grid((n + 127) / 128, STAT_SPLITS);
-  absstat_partial_kernel<T><<<grid, 256, 0, st>>>((const T*)x, ldx, L, n, mode, partial);
-  absstat_combine_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(partial, n, L, mode, (T*)acc);
+  ASVD_LAUNCH(K_STAT, st, (absstat_partial_kernel<T><<<grid, 256, 0, st>>>((const T*)x, ldx, L, n, mode, partial)));
+  ASVD_LAUNCH(K_STAT, st, (absstat_combine_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(partial, n, L, mode, (T*)acc)));
   ASVD_CUDA_CHECK(cudaGetLastError());
   return ASVD_OK;
 }
@@ -126,11 +126,15 @@ static int forward_run(const void* x, int64_t ldx, int64_t M, int n, const void*
   memset(&gb, 0, sizeof(gb));
   T* t = reinterpret_cast<T*>(scratch);
   // t[M, r] = x B^T  (materialised in the module dtype, as upstream's BLinear output is)
+  prof_begin(K_FORWARD, st);
   cudaError_t e = launch_gemm128<T, T, T, false>((const T*)x, ldx, (const T*)B, ldb, t, r, (int)M, r, n, nullptr, nullptr,
                                                  (const T*)nullptr, 1, gb, st);
+  prof_end(K_FORWARD, st);
   ASVD_CUDA_CHECK(e);
+  prof_begin(K_FORWARD, st);
   // y[M, m] = t A^T + bias
   e = launch_gemm128<T, T, T, false>(t, r, (const T*)A, lda, (T*)y, ldy, (int)M, m, r, nullptr, nullptr, (const T*)bias, 1, gb, st);
+  prof_end(K_FORWARD, st);
   ASVD_CUDA_CHECK(e);
   return ASVD_OK;
 }

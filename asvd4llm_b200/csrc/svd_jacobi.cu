@@ -8,8 +8,8 @@
 // One round (nv_pad/JB - 1 rounds per sweep, nv_pad/(2*JB) disjoint block pairs per round, all pairs of all
 // matrices of the batch in the same launch):
 //   gram_kernel   : partial Gram matrices G_c = P_c P_c^T of each 128-vector panel over 512-column chunks
-//   solve_kernel  : G = sum_c G_c in shared memory; cyclic two-sided Jacobi on the 128x128 G with the
-//                   rotations accumulated in R; sort-by-norm swaps; Newton-Schulz polish of R
+//   solve_kernel  : G = sum_c G_c in shared memory; one odd-even sweep of two-sided Jacobi on the 128x128 G,
+//                   rotations accumulated in a register-resident R; sort by norm; Newton-Schulz polish of R
 //   update_kernel : panel <- R^T panel  (in place, cp.async double-buffered column tiles)
 // After convergence (max |cos| < tol at visit time over one whole sweep) the rows of X are sigma_j * u_j.
 // The second factor is NOT accumulated: it is recovered from the ORIGINAL weight with one fp32 GEMM
@@ -17,6 +17,8 @@
 #include <stdarg.h>
 #include <float.h>
 #include <vector>
+#include <atomic>
+#include <utility>
 #include "common.cuh"
 #include "gemm_simt.cuh"
 
@@ -31,6 +33,44 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* last_error() { return g_err; }
+
+// ------------------------------------------------------------------------------------------------ profiling
+static std::atomic<unsigned long long> g_launches[K_COUNT];
+static bool g_prof_on = false;
+static double g_prof_ms[K_COUNT];
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_ev[K_COUNT];
+void prof_begin(int kind, cudaStream_t st) {
+  g_launches[kind].fetch_add(1, std::memory_order_relaxed);
+  if (!g_prof_on) return;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  cudaEventRecord(a, st);
+  g_prof_ev[kind].push_back({a, b});
+}
+void prof_end(int kind, cudaStream_t st) {
+  if (!g_prof_on) return;
+  cudaEventRecord(g_prof_ev[kind].back().second, st);
+}
+void prof_collect() {
+  if (!g_prof_on) return;
+  for (int k = 0; k < K_COUNT; ++k) {
+    for (auto& e : g_prof_ev[k]) {
+      float ms = 0.f;
+      cudaEventSynchronize(e.second);
+      cudaEventElapsedTime(&ms, e.first, e.second);
+      g_prof_ms[k] += ms;
+      cudaEventDestroy(e.first); cudaEventDestroy(e.second);
+    }
+    g_prof_ev[k].clear();
+  }
+}
+void prof_reset(bool on) {
+  prof_collect();
+  g_prof_on = on;
+  for (int k = 0; k < K_COUNT; ++k) g_prof_ms[k] = 0.0;
+}
+double prof_ms(int k) { return g_prof_ms[k]; }
+unsigned long long launches(int k) { return g_launches[k].load(); }
 
 // ------------------------------------------------------------------------------------------------ plan
 SvdPlan make_plan(int m, int n, int batch) {
@@ -170,28 +210,57 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, 
 }
 
 // ------------------------------------------------------------------------------------------------ solve
+// One CTA per block pair.  G = sum of the partial Grams (upper triangle kept) lives in shared memory and is
+// driven to diagonal form by ONE cyclic sweep of two-sided Jacobi in the odd-even ordering with a mandatory
+// exchange after every rotation (pairs (2t,2t+1) on even steps, (2t+1,2t+2) on odd steps; after JK steps every
+// pair has met once and the order is reversed).  Positions are therefore STATIC, which lets the accumulated
+// rotation R live in registers: warps 0-3 hold one row of R per thread (128 registers) and apply the 64
+// column rotations of a step with no data movement at all; warps 4-11 apply J^T G J to the upper triangle of
+// G in shared memory (float2 accesses on even steps).  Afterwards the columns are ordered by descending norm
+// (de Rijk's sorting, applied to the whole 128-column pair at once) and R is re-orthogonalised by one
+// Newton-Schulz step, R <- R (1.5 I - 0.5 R^T R): fp32 rounding in the ~130 accumulated rotations per column
+// leaves |R^T R - I| ~ 1e-5, which would otherwise drift the singular values (measured: 2e-4 -> 3e-6).
 constexpr int SLD = JK + 4;   // shared leading dimension (float4-aligned rows, 4-bank skew)
-constexpr int SOLVE_THREADS = 1024;
-constexpr size_t SOLVE_SMEM = sizeof(float) * (2 * JK * SLD) + sizeof(float2) * (JK / 2) + sizeof(float) * 64;
+constexpr int SOLVE_THREADS = 384;
+constexpr int SOLVE_RTHREADS = 128;
+constexpr int SOLVE_GTHREADS = SOLVE_THREADS - SOLVE_RTHREADS;
+constexpr int NB_EVEN = (JK / 2) * (JK / 2 + 1) / 2;       // 2080 upper-triangle 2x2 blocks on even steps
+constexpr int NB_ODD = (JK / 2 - 1) * (JK / 2) / 2;        // 2016 on odd steps (positions 0 and JK-1 idle)
+constexpr size_t SOLVE_SMEM = sizeof(float) * (2 * JK * SLD) + sizeof(float2) * (JK / 2) + sizeof(float) * 64 +
+                              sizeof(uchar2) * (NB_EVEN + NB_ODD) + sizeof(int) * JK + sizeof(float) * JK;
 
-// round-robin (circle method) pairing of JK indices: step st in [0, JK-1), slot i in [0, JK/2)
-__device__ __forceinline__ void rr_pair(int st, int i, int& p, int& q) {
-  constexpr int N1 = JK - 1;
-  int a, b;
-  if (i == 0) { a = N1; b = st; }
-  else { a = st + i; if (a >= N1) a -= N1; b = st - i; if (b < 0) b += N1; }
-  p = min(a, b); q = max(a, b);
+__device__ __forceinline__ float2 jacobi_cs(float app, float aqq, float apq) {
+  float c = 1.f, s = 0.f;
+  if (fabsf(apq) > 1e-8f * sqrtf(fmaxf(app, 0.f) * fmaxf(aqq, 0.f)) && apq != 0.f) {
+    float tau = (aqq - app) / (2.f * apq);
+    float t = copysignf(1.f, tau) / (fabsf(tau) + sqrtf(1.f + tau * tau));
+    c = rsqrtf(1.f + t * t);
+    s = t * c;
+  }
+  return make_float2(c, s);
 }
+
+// rotation + exchange of one position pair of a row of R: (a, b) <- (s a + c b, c a - s b)
+#define ASVD_ROT_SWAP(a, b, cs_)            \
+  do {                                      \
+    const float _a = (a), _b = (b);         \
+    (a) = fmaf((cs_).y, _a, (cs_).x * _b);  \
+    (b) = fmaf((cs_).x, _a, -(cs_).y * _b); \
+  } while (0)
 
 __global__ void __launch_bounds__(SOLVE_THREADS, 1)
 solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, float* __restrict__ Rout,
              int* __restrict__ pairflag, unsigned* __restrict__ maxoff_bits, int* __restrict__ status,
              const int* __restrict__ done, float tol) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* G = reinterpret_cast<float*>(smem_raw);
-  float* R = G + JK * SLD;
-  float2* cs = reinterpret_cast<float2*>(R + JK * SLD);
-  float* red = reinterpret_cast<float*>(cs + JK / 2);
+  float* G = reinterpret_cast<float*>(smem_raw);            // [JK][SLD]; later E = R^T R
+  float* Rs = G + JK * SLD;                                 // [JK][SLD]; R in sorted column order (after the sweep)
+  float2* cs = reinterpret_cast<float2*>(Rs + JK * SLD);    // [JK/2]
+  float* red = reinterpret_cast<float*>(cs + JK / 2);       // [64]
+  uchar2* tab_even = reinterpret_cast<uchar2*>(red + 64);   // [NB_EVEN] (s, t) of each upper-triangle block
+  uchar2* tab_odd = tab_even + NB_EVEN;                     // [NB_ODD]
+  int* dest = reinterpret_cast<int*>(tab_odd + NB_ODD);     // [JK] output column of each position
+  float* diag = reinterpret_cast<float*>(dest + JK);        // [JK]
 
   const int b = blockIdx.y, p = blockIdx.x;
   if (done[b]) return;
@@ -203,7 +272,14 @@ solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, flo
     float s = 0.f;
     for (int c = 0; c < chunks; ++c) s += Gp[(int64_t)c * (JK * JK) + e];
     G[(e >> 7) * SLD + (e & (JK - 1))] = s;
-    R[(e >> 7) * SLD + (e & (JK - 1))] = ((e >> 7) == (e & (JK - 1))) ? 1.f : 0.f;
+  }
+  if (tid < JK / 2) {            // block tables: row s of the triangle starts at s*n - s(s-1)/2
+    int off = tid * (JK / 2) - tid * (tid - 1) / 2;
+    for (int t = tid; t < JK / 2; ++t) tab_even[off + (t - tid)] = make_uchar2(tid, t);
+    if (tid < JK / 2 - 1) {
+      off = tid * (JK / 2 - 1) - tid * (tid - 1) / 2;
+      for (int t = tid; t < JK / 2 - 1; ++t) tab_odd[off + (t - tid)] = make_uchar2(tid, t);
+    }
   }
   __syncthreads();
   // convergence measure of this pair at visit time: max |cos| between any two of its 128 vectors
@@ -213,7 +289,7 @@ solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, flo
     int r = e >> 7, c = e & (JK - 1);
     float g = G[r * SLD + c];
     if (!(fabsf(g) <= FLT_MAX)) bad = 1;
-    if (r != c) {
+    if (r < c) {
       float d = G[r * SLD + r] * G[c * SLD + c];
       if (d > 0.f) mx = fmaxf(mx, fabsf(g) * rsqrtf(d));
     }
@@ -223,8 +299,8 @@ solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, flo
   if ((tid & 31) == 0) { red[tid >> 5] = mx; red[32 + (tid >> 5)] = bad ? 1.f : 0.f; }
   __syncthreads();
   if (tid < 32) {
-    float v = warp_max(red[tid]);
-    float bb = warp_max(red[32 + tid]);
+    float v = warp_max(tid < SOLVE_THREADS / 32 ? red[tid] : 0.f);
+    float bb = warp_max(tid < SOLVE_THREADS / 32 ? red[32 + tid] : 0.f);
     if (tid == 0) { red[0] = v; red[32] = bb; }
   }
   __syncthreads();
@@ -241,67 +317,106 @@ solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, flo
   }
   if (tid == 0) pairflag[idx] = 1;
 
-  const int nsweeps = (mx > 1e-3f) ? 2 : 1;
-  for (int sw = 0; sw < nsweeps; ++sw) {
-    for (int st = 0; st < JK - 1; ++st) {
-      if (tid < JK / 2) {
-        int pp, qq;
-        rr_pair(st, tid, pp, qq);
-        float app = G[pp * SLD + pp], aqq = G[qq * SLD + qq], apq = G[pp * SLD + qq];
-        float c = 1.f, s = 0.f, tt = 0.f;
-        if (fabsf(apq) > 1e-8f * sqrtf(fmaxf(app, 0.f) * fmaxf(aqq, 0.f)) && apq != 0.f) {
-          float tau = (aqq - app) / (2.f * apq);
-          tt = copysignf(1.f, tau) / (fabsf(tau) + sqrtf(1.f + tau * tau));
-          c = rsqrtf(1.f + tt * tt);
-          s = tt * c;
-        }
-        // keep the larger norm at the lower index (de Rijk): extra quarter turn when out of order
-        if (app - tt * apq < aqq + tt * apq) { float c2 = s, s2 = -c; c = c2; s = s2; }
-        cs[tid] = make_float2(c, s);
+  // ---- one odd-even sweep
+  float r[JK];                                   // row `tid` of R (warps 0-3 only)
+  if (tid < SOLVE_RTHREADS) {
+#pragma unroll
+    for (int j = 0; j < JK; ++j) r[j] = (j == tid) ? 1.f : 0.f;
+  }
+  const int gt = tid - SOLVE_RTHREADS;           // index among the G threads (negative for R threads)
+  for (int st2 = 0; st2 < JK / 2; ++st2) {
+#pragma unroll 1
+    for (int odd = 0; odd < 2; ++odd) {
+      const int npairs = JK / 2 - odd;
+      if (gt >= 0 && gt < npairs) {
+        const int pp = 2 * gt + odd;
+        cs[gt] = jacobi_cs(G[pp * SLD + pp], G[(pp + 1) * SLD + pp + 1], G[pp * SLD + pp + 1]);
       }
       __syncthreads();
-      // G <- J^T G J, one 2x2 block per (row pair, column pair)
+      if (tid < SOLVE_RTHREADS) {
+        if (odd == 0) {
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int si = (tid >> 6) + 16 * it, ti = tid & 63;
-        int ps, qs, pt, qt;
-        rr_pair(st, si, ps, qs);
-        rr_pair(st, ti, pt, qt);
-        const float2 a = cs[si], bq = cs[ti];
-        float g00 = G[ps * SLD + pt], g01 = G[ps * SLD + qt], g10 = G[qs * SLD + pt], g11 = G[qs * SLD + qt];
-        float r00 = a.x * g00 - a.y * g10, r01 = a.x * g01 - a.y * g11;
-        float r10 = a.y * g00 + a.x * g10, r11 = a.y * g01 + a.x * g11;
-        float o00 = bq.x * r00 - bq.y * r01, o01 = bq.y * r00 + bq.x * r01;
-        float o10 = bq.x * r10 - bq.y * r11, o11 = bq.y * r10 + bq.x * r11;
-        if (si == ti) { o01 = 0.f; o10 = 0.f; }
-        G[ps * SLD + pt] = o00; G[ps * SLD + qt] = o01; G[qs * SLD + pt] = o10; G[qs * SLD + qt] = o11;
-      }
-      // R <- R J
+          for (int t = 0; t < JK / 2; ++t) { const float2 q = cs[t]; ASVD_ROT_SWAP(r[2 * t], r[2 * t + 1], q); }
+        } else {
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int i = (tid >> 6) + 16 * it, ti = tid & 63;
-        int pt, qt;
-        rr_pair(st, ti, pt, qt);
-        const float2 bq = cs[ti];
-        float r0 = R[i * SLD + pt], r1 = R[i * SLD + qt];
-        R[i * SLD + pt] = bq.x * r0 - bq.y * r1;
-        R[i * SLD + qt] = bq.y * r0 + bq.x * r1;
+          for (int t = 0; t < JK / 2 - 1; ++t) { const float2 q = cs[t]; ASVD_ROT_SWAP(r[2 * t + 1], r[2 * t + 2], q); }
+        }
+      } else {
+        const uchar2* tab = odd ? tab_odd : tab_even;
+        const int nblk = odd ? NB_ODD : NB_EVEN;
+        for (int i = gt; i < nblk; i += SOLVE_GTHREADS) {
+          const uchar2 stp = tab[i];
+          const int ps = 2 * stp.x + odd, pt = 2 * stp.y + odd;
+          const float2 a = cs[stp.x], bq = cs[stp.y];
+          float g00, g01, g10, g11;
+          float* row0 = &G[ps * SLD + pt];
+          float* row1 = row0 + SLD;
+          if (odd == 0) {
+            float2 u = *reinterpret_cast<const float2*>(row0), v = *reinterpret_cast<const float2*>(row1);
+            g00 = u.x; g01 = u.y; g10 = v.x; g11 = v.y;
+          } else {
+            g00 = row0[0]; g01 = row0[1]; g10 = row1[0]; g11 = row1[1];
+          }
+          if (stp.x == stp.y) g10 = g01;                       // lower triangle is not stored
+          // rows: (new at ps, new at ps+1) = (s g0 + c g1, c g0 - s g1)   [rotation, then exchange]
+          const float y00 = fmaf(a.y, g00, a.x * g10), y01 = fmaf(a.y, g01, a.x * g11);
+          const float y10 = fmaf(a.x, g00, -a.y * g10), y11 = fmaf(a.x, g01, -a.y * g11);
+          // columns, same rule
+          float o00 = fmaf(bq.y, y00, bq.x * y01), o01 = fmaf(bq.x, y00, -bq.y * y01);
+          float o10 = fmaf(bq.y, y10, bq.x * y11), o11 = fmaf(bq.x, y10, -bq.y * y11);
+          if (stp.x == stp.y) { o01 = 0.f; o10 = 0.f; }
+          if (odd == 0) {
+            *reinterpret_cast<float2*>(row0) = make_float2(o00, o01);
+            *reinterpret_cast<float2*>(row1) = make_float2(o10, o11);
+          } else {
+            row0[0] = o00; row0[1] = o01; row1[0] = o10; row1[1] = o11;
+          }
+        }
+        if (odd && gt < JK - 2) {
+          // positions 0 and JK-1 sit out on odd steps, but row 0 still takes the column rotations and column JK-1
+          // the row rotations of the active pairs
+          const int t = gt < JK / 2 - 1 ? gt : gt - (JK / 2 - 1);
+          const float2 q = cs[t];
+          const int pp = 2 * t + 1;
+          float* e0 = gt < JK / 2 - 1 ? &G[pp] : &G[pp * SLD + JK - 1];
+          float* e1 = gt < JK / 2 - 1 ? e0 + 1 : e0 + SLD;
+          const float g0 = *e0, g1 = *e1;
+          *e0 = fmaf(q.y, g0, q.x * g1);
+          *e1 = fmaf(q.x, g0, -q.y * g1);
+        }
       }
       __syncthreads();
     }
   }
-  // Newton-Schulz polish: R <- R (1.5 I - 0.5 R^T R) restores the orthogonality lost to fp32 rounding in the
-  // ~250 accumulated rotations per column (measured 1e-5 -> 4e-7), which otherwise drifts the singular values.
-  const int ta = tid >> 5, tb = tid & 31;
-  {
+  // ---- order the columns by descending norm, re-orthogonalise, write R
+  if (tid < JK) diag[tid] = G[tid * SLD + tid];
+  __syncthreads();
+  if (tid < JK) {
+    const float d = diag[tid];
+    int rank = 0;
+    for (int j = 0; j < JK; ++j) {
+      const float e = diag[j];
+      rank += (e > d) || (e == d && j < tid);
+    }
+    dest[tid] = rank;
+  }
+  __syncthreads();
+  if (tid < SOLVE_RTHREADS) {
+#pragma unroll
+    for (int j = 0; j < JK; ++j) Rs[tid * SLD + dest[j]] = r[j];
+  }
+  __syncthreads();
+  float* E = G;
+  for (int tile = tid; tile < (JK / 4) * (JK / 4); tile += SOLVE_THREADS) {
+    const int ta = tile >> 5, tb = tile & 31;
     float e[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) e[i][j] = 0.f;
     for (int l = 0; l < JK; ++l) {
-      float4 a = *reinterpret_cast<const float4*>(&R[l * SLD + ta * 4]);
-      float4 bb = *reinterpret_cast<const float4*>(&R[l * SLD + tb * 4]);
+      float4 a = *reinterpret_cast<const float4*>(&Rs[l * SLD + ta * 4]);
+      float4 bb = *reinterpret_cast<const float4*>(&Rs[l * SLD + tb * 4]);
       float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -310,32 +425,33 @@ solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, flo
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-      *reinterpret_cast<float4*>(&G[(ta * 4 + i) * SLD + tb * 4]) = make_float4(e[i][0], e[i][1], e[i][2], e[i][3]);
+      *reinterpret_cast<float4*>(&E[(ta * 4 + i) * SLD + tb * 4]) = make_float4(e[i][0], e[i][1], e[i][2], e[i][3]);
   }
   __syncthreads();
-  {
+  float* Ro = Rout + (int64_t)idx * (JK * JK);
+  for (int tile = tid; tile < (JK / 4) * (JK / 4); tile += SOLVE_THREADS) {
+    const int ta = tile >> 5, tb = tile & 31;
     float o[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
     for (int l = 0; l < JK; ++l) {
-      float4 bb = *reinterpret_cast<const float4*>(&G[l * SLD + tb * 4]);
+      float4 bb = *reinterpret_cast<const float4*>(&E[l * SLD + tb * 4]);
       float bv[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float a = R[(ta * 4 + i) * SLD + l];
+        float a = Rs[(ta * 4 + i) * SLD + l];
 #pragma unroll
         for (int j = 0; j < 4; ++j) o[i][j] = fmaf(a, bv[j], o[i][j]);
       }
     }
-    float* Ro = Rout + (int64_t)idx * (JK * JK);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      float4 r = *reinterpret_cast<const float4*>(&R[(ta * 4 + i) * SLD + tb * 4]);
+      float4 rr = *reinterpret_cast<const float4*>(&Rs[(ta * 4 + i) * SLD + tb * 4]);
       *reinterpret_cast<float4*>(&Ro[(ta * 4 + i) * JK + tb * 4]) =
-          make_float4(1.5f * r.x - 0.5f * o[i][0], 1.5f * r.y - 0.5f * o[i][1], 1.5f * r.z - 0.5f * o[i][2],
-                      1.5f * r.w - 0.5f * o[i][3]);
+          make_float4(1.5f * rr.x - 0.5f * o[i][0], 1.5f * rr.y - 0.5f * o[i][1], 1.5f * rr.z - 0.5f * o[i][2],
+                      1.5f * rr.w - 0.5f * o[i][3]);
     }
   }
 }
@@ -429,9 +545,12 @@ update_kernel(float* __restrict__ X, int64_t mat_stride, int ldx, const int2* __
 
 // ------------------------------------------------------------------------------------------------ finalize
 // per-row 2-norm; optionally normalises the row in place.  One CTA per row.
+// `anchor` (optional): the Jacobi column norm of the same vector.  |Y_j| recomputed from the original weight is
+// free of accumulated rotation drift but, for sigma_j below ~eps*sigma_max, it is dominated by leakage from the
+// large directions; one-sided Jacobi norms keep high relative accuracy there, so they win when the two disagree.
 __global__ void __launch_bounds__(256) rownorm_kernel(float* __restrict__ X, int64_t mat_stride, int ld, int len,
                                                       int normalise, float* __restrict__ norm_out, int nv_pad,
-                                                      int* __restrict__ status) {
+                                                      int* __restrict__ status, const float* __restrict__ anchor) {
   __shared__ float red[8];
   const int b = blockIdx.y, j = blockIdx.x;
   float* row = X + b * mat_stride + (int64_t)j * ld;
@@ -446,7 +565,11 @@ __global__ void __launch_bounds__(256) rownorm_kernel(float* __restrict__ X, int
     if (threadIdx.x == 0) red[0] = v;
   }
   __syncthreads();
-  const float nrm = sqrtf(red[0]);
+  float nrm = sqrtf(red[0]);
+  if (anchor) {
+    const float a = anchor[(int64_t)b * nv_pad + j];
+    if (!(fabsf(nrm - a) <= 1e-3f * a)) nrm = (a <= FLT_MAX && nrm <= FLT_MAX) ? a : nrm;
+  }
   if (threadIdx.x == 0) {
     norm_out[(int64_t)b * nv_pad + j] = nrm;
     if (!(nrm <= FLT_MAX)) atomicOr(&status[b], 1);
@@ -584,7 +707,7 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
   ASVD_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int) * p.batch, st));
   {
     dim3 grid((p.n + 31) / 32, (p.m + 31) / 32, p.batch);
-    prep_kernel<T><<<grid, 256, 0, st>>>(d_W, scale, ldw, p.m, p.n, p.tall, X, xs, p.len_pad);
+    ASVD_LAUNCH(K_PREP, st, (prep_kernel<T><<<grid, 256, 0, st>>>(d_W, scale, ldw, p.m, p.n, p.tall, X, xs, p.len_pad)));
     ASVD_CUDA_CHECK(cudaGetLastError());
   }
   std::vector<unsigned> h_maxoff(p.batch);
@@ -595,10 +718,10 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
     ASVD_CUDA_CHECK(cudaMemsetAsync(maxoff, 0, sizeof(unsigned) * p.batch, st));
     for (int r = 0; r < p.rounds; ++r) {
       const int2* pr = d_pairs + (size_t)r * p.pairs;
-      gram_kernel<<<dim3(p.chunks, p.pairs, p.batch), 256, 0, st>>>(X, xs, p.len_pad, pr, p.len_pad, p.chunks, p.pairs, G, done);
-      solve_kernel<<<dim3(p.pairs, p.batch), SOLVE_THREADS, SOLVE_SMEM, st>>>(G, p.chunks, p.pairs, R, flag, maxoff, status, done, tol);
+      ASVD_LAUNCH(K_GRAM, st, (gram_kernel<<<dim3(p.chunks, p.pairs, p.batch), 256, 0, st>>>(X, xs, p.len_pad, pr, p.len_pad, p.chunks, p.pairs, G, done)));
+      ASVD_LAUNCH(K_SOLVE, st, (solve_kernel<<<dim3(p.pairs, p.batch), SOLVE_THREADS, SOLVE_SMEM, st>>>(G, p.chunks, p.pairs, R, flag, maxoff, status, done, tol)));
       const int ctas_x = (p.len_pad / 128 + UPD_TILES - 1) / UPD_TILES;
-      update_kernel<<<dim3(ctas_x, p.pairs, p.batch), 256, UPDATE_SMEM, st>>>(X, xs, p.len_pad, pr, p.len_pad, p.pairs, R, flag, done);
+      ASVD_LAUNCH(K_UPDATE, st, (update_kernel<<<dim3(ctas_x, p.pairs, p.batch), 256, UPDATE_SMEM, st>>>(X, xs, p.len_pad, pr, p.len_pad, p.pairs, R, flag, done)));
     }
     ASVD_CUDA_CHECK(cudaGetLastError());
     ASVD_CUDA_CHECK(cudaMemcpyAsync(h_maxoff.data(), maxoff, sizeof(unsigned) * p.batch, cudaMemcpyDeviceToHost, st));
@@ -617,7 +740,7 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
       ASVD_CUDA_CHECK(cudaMemcpyAsync(done, h_done.data(), sizeof(int) * p.batch, cudaMemcpyHostToDevice, st));
   }
   // rows of X are sigma_j u_j: normalise, recover the other factor from the original weight, anchor sigma to it
-  rownorm_kernel<<<dim3(p.nv_pad, p.batch), 256, 0, st>>>(X, xs, p.len_pad, p.len_pad, 1, norm, p.nv_pad, status);
+  ASVD_LAUNCH(K_FINAL, st, (rownorm_kernel<<<dim3(p.nv_pad, p.batch), 256, 0, st>>>(X, xs, p.len_pad, p.len_pad, 1, sigma, p.nv_pad, status, nullptr)));
   ASVD_CUDA_CHECK(cudaGetLastError());
   {
     GemmBatch gb;
@@ -633,26 +756,29 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
       g1.Bptrs = d_W + b;
       const float* sb = scale + (int64_t)b * p.n;
       cudaError_t e;
+      prof_begin(K_FINAL, st);
       if (p.tall)   // Y[j][l] = sum_i Xhat[j][i] W[i][l] * s[l]
         e = launch_gemm128<float, T, float, true>(X + b * xs, p.len_pad, (const T*)nullptr, ldw, Y + b * gb.strideC, p.ldy,
                                                   p.nv_pad, p.n, p.m, nullptr, sb, nullptr, 1, g1, st);
       else          // Y[j][i] = sum_l Xhat[j][l] s[l] W[i][l]
         e = launch_gemm128<float, T, float, false>(X + b * xs, p.len_pad, (const T*)nullptr, ldw, Y + b * gb.strideC, p.ldy,
                                                    p.nv_pad, p.m, p.n, sb, nullptr, nullptr, 1, g1, st);
+      prof_end(K_FINAL, st);
       ASVD_CUDA_CHECK(e);
     }
   }
-  rownorm_kernel<<<dim3(p.nv_pad, p.batch), 256, 0, st>>>(Y, (int64_t)p.nv_pad * p.ldy, p.ldy, p.nv, 0, norm, p.nv_pad, status);
+  ASVD_LAUNCH(K_FINAL, st, (rownorm_kernel<<<dim3(p.nv_pad, p.batch), 256, 0, st>>>(Y, (int64_t)p.nv_pad * p.ldy, p.ldy, p.nv, 0, norm, p.nv_pad, status, sigma)));
   ASVD_CUDA_CHECK(cudaGetLastError());
   {
     int P = 1;
     while (P < p.nv_pad) P <<= 1;
-    sort_kernel<<<p.batch, 1024, 8 * (size_t)P, st>>>(norm, sigma, perm, p.nv, p.nv_pad, P);
+    ASVD_LAUNCH(K_FINAL, st, (sort_kernel<<<p.batch, 1024, 8 * (size_t)P, st>>>(norm, sigma, perm, p.nv, p.nv_pad, P)));
     ASVD_CUDA_CHECK(cudaGetLastError());
   }
   std::vector<int> h_status(p.batch);
   ASVD_CUDA_CHECK(cudaMemcpyAsync(h_status.data(), status, sizeof(int) * p.batch, cudaMemcpyDeviceToHost, st));
   ASVD_CUDA_CHECK(cudaStreamSynchronize(st));
+  prof_collect();
   if (sweeps_out) for (int b = 0; b < p.batch; ++b) sweeps_out[b] = h_sweeps[b];
   for (int b = 0; b < p.batch; ++b)
     if (h_status[b]) { set_error("non-finite values in weight %d of the batch (or its scale)", b); return ASVD_ERR_NONFINITE; }
@@ -677,12 +803,12 @@ static int do_extract(const SvdPlan& p, const unsigned char* ws, int b, int r, i
   dim3 gA((r + 31) / 32, (p.m + 31) / 32), gB((p.n + 255) / 256, r);
   if (p.tall) {
     // X rows are unit u_j (length m); Y rows are sigma_j v_j^T diag(s) (length n)
-    extract_cols_kernel<TC><<<gA, 256, 0, st>>>(X, p.len_pad, perm, sigma, a, p.m, r, A, lda);
-    extract_rows_kernel<TC><<<gB, 256, 0, st>>>(Y, p.ldy, perm, sigma, -a, scale, p.n, r, B, ldb);
+    ASVD_LAUNCH(K_EXTRACT, st, (extract_cols_kernel<TC><<<gA, 256, 0, st>>>(X, p.len_pad, perm, sigma, a, p.m, r, A, lda)));
+    ASVD_LAUNCH(K_EXTRACT, st, (extract_rows_kernel<TC><<<gB, 256, 0, st>>>(Y, p.ldy, perm, sigma, -a, scale, p.n, r, B, ldb)));
   } else {
     // X rows are unit v_j^T diag(s)... scaled space (length n); Y rows are sigma_j u_j (length m)
-    extract_cols_kernel<TC><<<gA, 256, 0, st>>>(Y, p.ldy, perm, sigma, a - 1.f, p.m, r, A, lda);
-    extract_rows_kernel<TC><<<gB, 256, 0, st>>>(X, p.len_pad, perm, sigma, 1.f - a, scale, p.n, r, B, ldb);
+    ASVD_LAUNCH(K_EXTRACT, st, (extract_cols_kernel<TC><<<gA, 256, 0, st>>>(Y, p.ldy, perm, sigma, a - 1.f, p.m, r, A, lda)));
+    ASVD_LAUNCH(K_EXTRACT, st, (extract_rows_kernel<TC><<<gB, 256, 0, st>>>(X, p.len_pad, perm, sigma, 1.f - a, scale, p.n, r, B, ldb)));
   }
   ASVD_CUDA_CHECK(cudaGetLastError());
   return ASVD_OK;
@@ -692,6 +818,21 @@ extern "C" {
 
 int asvd_version(void) { return ASVD_B200_VERSION; }
 const char* asvd_last_error(void) { return asvd::last_error(); }
+
+void asvd_profile_enable(int on) { asvd::prof_reset(on != 0); }
+int asvd_profile_read(double* ms_out, uint64_t* launches_out) {
+  asvd::prof_collect();
+  for (int k = 0; k < asvd::K_COUNT; ++k) {
+    if (ms_out) ms_out[k] = asvd::prof_ms(k);
+    if (launches_out) launches_out[k] = asvd::launches(k);
+  }
+  return asvd::K_COUNT;
+}
+uint64_t asvd_launch_count(void) {
+  uint64_t t = 0;
+  for (int k = 0; k < asvd::K_COUNT; ++k) t += asvd::launches(k);
+  return t;
+}
 
 int asvd_rank_for_ratio(int64_t out_features, int64_t in_features, double param_ratio, int rank_align) {
   // modules/svd_linear.py:39-44: int(n_params * ratio) // (in + out), then ceil to a multiple of rank_align

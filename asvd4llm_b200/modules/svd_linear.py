@@ -87,7 +87,13 @@ def _stat(linear, name):
 
 def _key(linear, act_aware, alpha):
     def sig(t):
-        return None if t is None else (t.data_ptr(), t._version, tuple(t.shape), t.dtype)
+        # `.data` mutations bypass autograd's version counter, so a cheap content fingerprint (strided sample)
+        # guards the cache against in-place edits of the weight or of the statistics
+        if t is None:
+            return None
+        flat = t.detach().reshape(-1)
+        sample = flat[:: max(1, flat.numel() // 4096)].double()
+        return (t.data_ptr(), tuple(t.shape), t.dtype, float(sample.sum()), float(sample.abs().sum()))
     w = linear.weight
     return (id(linear), sig(w.data), bool(act_aware), float(alpha) if act_aware else None,
             sig(_stat(linear, "scaling_diag_matrix")) if act_aware else None,

@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on BASELINE.json's config.
+
+  python bench.py --gpus N --steps K --warmup W            (our arm; torchrun launches N>1, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K --warmup W   (the reference's CPU algorithm, rank 0 only)
+
+Metric: weight matrices factorised per second.  Workload (configs[1]): 4096x4096 fp16 weights, activation
+scale s = sdm**0.5 + 1e-6, param_ratio 0.9 -> rank 1843, sigma_fuse "UV", factors written in fp16.
+A step = one batch of `--batch` such weights per GPU through the whole hot path (scaling vector -> scaled SVD
+-> truncation / un-scaling / sigma fusion / cast).  `value` times it with everything resident in HBM;
+`e2e` goes through the public module API (SVDLinear.from_linear semantics, batched) with the weights in pinned
+HOST memory and the factors copied back to the host, copies inside the timed region.
+Each rank works on its own weights (no data-path collective): scaling is "weak".
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M, N_IN, RATIO, ALPHA = 4096, 4096, 0.9, 0.5
+METRIC = "weight-matrices factorised/sec (full-model ASVD wall-clock) at 1/2/4/8 GPU"
+UNIT = "matrices/s"
+WORKLOAD = "single 4096x4096 fp16 weight: activation-scaled SVD + rank-1843 truncation (param_ratio 0.9, alpha 0.5, sigma_fuse UV)"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return p.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc, self.index = None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        self.result = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            return
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            self.result = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                           "samples": len(sm)}
+
+
+def reference_step(lin, O):
+    """One unit of the reference's CPU path (modules/svd_linear.py:26-103 as shipped: scale, svd_lowrank, fuse)."""
+    return O.from_linear(lin, RATIO, act_aware=True, alpha=ALPHA, sigma_fuse="UV", method="lowrank")
+
+
+def make_cpu_linear(seed):
+    import torch.nn as nn
+    g = torch.Generator().manual_seed(seed)
+    lin = nn.Linear(N_IN, M, bias=False)
+    lin.weight.data = (torch.randn(M, N_IN, generator=g) * 0.02).half()
+    lin.scaling_diag_matrix = torch.exp(torch.randn(N_IN, generator=g)).half()
+    return lin
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import asvd_oracle as O
+    torch.manual_seed(233)
+    lin = make_cpu_linear(233)
+    for _ in range(max(1, min(args.warmup, 1))):       # one warm-up is enough for a CPU LAPACK path
+        reference_step(lin, O)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        reference_step(lin, O)
+    dt = time.perf_counter() - t0
+    value = args.steps / dt
+    cores = torch.get_num_threads()
+    sample = f"{args.steps} x one 4096x4096 fp16 weight @0.9 per step (scale, svd_lowrank q=1843 niter=2, un-scale, fuse, cast)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_step": 1, "where": "host CPU, oracle port of the upstream algorithm"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4, help="same-shape weights per step per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from asvd4llm_b200 import _lib
+    from asvd4llm_b200.modules.svd_linear import from_linear_batch
+    import torch.nn as nn
+    _lib.load()
+    B = args.batch
+    r = _lib.rank_for_ratio(M, N_IN, RATIO, 1)
+    g = torch.Generator(device=dev).manual_seed(233 + rank)
+    n_pool = 2                                            # alternate two input sets; the 4 x 128 MB fp32 working set
+    pools = []                                            # per step is itself 4x larger than the 126 MB L2
+    for _ in range(n_pool):
+        Ws = [(torch.randn(M, N_IN, device=dev, generator=g) * 0.02).half() for _ in range(B)]
+        sdm = [torch.exp(torch.randn(N_IN, device=dev, generator=g)).half() for _ in range(B)]
+        pools.append((Ws, sdm))
+
+    def device_step(i):
+        Ws, sdm = pools[i % n_pool]
+        scales = [_lib.scaling_vector(s, None, ALPHA, N_IN, dev) for s in sdm]
+        fact = _lib.scaled_svd(Ws, scales)
+        outs = [fact.extract(r, "UV", torch.float16, b) for b in range(B)]
+        return fact, outs
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        fact, _ = device_step(i)
+    barrier()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            fact, outs = device_step(i)
+        e1.record()
+        barrier()
+    launches = _lib.launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    sweeps = list(fact.sweeps)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- e2e: public module API, host-resident weights, factors read back to the host
+    lins = []
+    for b in range(B):
+        lin = nn.Linear(N_IN, M, bias=False)
+        lin.weight.data = pools[0][0][b].cpu().pin_memory()
+        lin.scaling_diag_matrix = pools[0][1][b].cpu().pin_memory()
+        lins.append(lin)
+
+    def e2e_step():
+        mods = from_linear_batch(lins, [RATIO] * B, act_aware=True, alpha=ALPHA, sigma_fuse="UV")
+        return sum(float(m.ALinear.weight[0, 0]) for m in mods)     # factors are host tensors here
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(1, min(args.steps, 3))
+    for _ in range(n_e2e):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * B * n_e2e / e2e_s
+    h2d = B * (M * N_IN * 2 + N_IN * 2)
+    d2h = B * (r * (M + N_IN) * 2)
+
+    # ---- roofline of the dominant kernel: per-class CUDA-event timing over the first sweeps (every pair active)
+    roofline, classes = None, None
+    if rank == 0:
+        _lib.profile_enable(True)
+        Ws, sdm = pools[0]
+        scales = [_lib.scaling_vector(s, None, ALPHA, N_IN, dev) for s in sdm]
+        before = _lib.profile_read()
+        _lib.scaled_svd(Ws, scales, max_sweeps=2)
+        torch.cuda.synchronize()
+        after = _lib.profile_read()
+        _lib.profile_enable(False)
+        classes = {k: {"ms": after[k][0], "launches": after[k][1] - before[k][1]} for k in after if after[k][1] > before[k][1]}
+        dom = max(("gram", "solve", "update"), key=lambda k: classes.get(k, {"ms": 0})["ms"])
+        nv = len_ = 4096
+        pairs, chunks, JK = nv // 128, len_ // 512, 128
+        bytes_per_launch = {
+            "update": B * (2 * nv * len_ * 4 + pairs * JK * JK * 4),           # read + write every panel, read R
+            "gram": B * (nv * len_ * 4 + pairs * chunks * JK * JK * 4),        # read every panel, write partial Grams
+            "solve": B * (pairs * chunks * JK * JK * 4 + pairs * JK * JK * 4),   # read partial Grams, write R
+        }[dom]
+        avg_s = classes[dom]["ms"] / classes[dom]["launches"] / 1e3
+        peak, which = peaks()
+        achieved = bytes_per_launch / avg_s / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(dom)
+        roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": which,
+                    "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_us": avg_s * 1e6,
+                    "class_ms_first_2_sweeps": {k: round(v["ms"], 3) for k, v in classes.items()}}
+
+    # ---- CPU baseline: the reference's algorithm (oracle port) on this box's host cores, rank 0, N=1 only
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import asvd_oracle as O
+        torch.manual_seed(233)
+        lin = make_cpu_linear(233)
+        reference_step(lin, O)
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter(); reference_step(lin, O); ts.append(time.perf_counter() - t0)
+        cpu_baseline = {"value": 1.0 / statistics.median(ts), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": "3 x one 4096x4096 fp16 weight @0.9 (scale, svd_lowrank q=1843 niter=2, un-scale, fuse, cast), median"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_step_per_gpu": B, "rank": r, "sweeps": sweeps,
+                       "l2": "inputs larger than L2: 4 x 128 MB fp32 working set per step vs 126 MB L2; two input sets alternate",
+                       "parallelism": f"{world} independent ranks, disjoint weights, no data-path collective"},
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": n_e2e, "api": "asvd4llm_b200.modules.svd_linear.from_linear_batch (SVDLinear.from_linear semantics)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks.result,
+        }))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -40,6 +40,15 @@ int asvd_version(void);
 /* thread-local description of the last non-zero status */
 const char* asvd_last_error(void);
 
+/* ---- measurement hooks (bench.py): kernel-launch counters and optional per-class CUDA-event timing.
+ * Classes, in order: prep, gram, solve, update, finalize, extract, forward, absstat (8 entries).
+ * asvd_profile_enable(1) resets the timers and makes every launch record an event pair (adds overhead:
+ * never enabled inside a timed region); asvd_profile_read fills ms_out[8] / launches_out[8] (either may be
+ * NULL) and returns the number of classes.  asvd_launch_count() = all launches since the library loaded. */
+void asvd_profile_enable(int on);
+int asvd_profile_read(double* ms_out, uint64_t* launches_out);
+uint64_t asvd_launch_count(void);
+
 /* ---- a2: rank formula — modules/svd_linear.py:39-44.  Host arithmetic, here so every binding agrees. */
 int asvd_rank_for_ratio(int64_t out_features, int64_t in_features, double param_ratio, int rank_align);
 

@@ -1,0 +1,309 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle.  Tolerances are north_star's:
+singular values within 1e-4 relative (all kept r), reconstructed W within 1e-3 Frobenius, forward within
+1e-3 max-abs in fp16 under the |y|<1 normalisation."""
+import argparse, contextlib, io, os
+import pytest, torch, torch.nn as nn
+from conftest import build_tiny_opt
+from oracle import asvd_oracle as O
+
+pytestmark = pytest.mark.gpu
+SIGMA_RTOL = 1e-4
+RECON_TOL = 1e-3
+
+
+def _lib():
+    from asvd4llm_b200 import _lib
+    return _lib
+
+
+def _scaled_norm(X, s):
+    return (X * s).norm()
+
+
+def check_factorisation(W, scale32, ratio, fuse="UV", out_dtype=torch.float32, rank_align=1, fact=None, b=0):
+    L = _lib()
+    m, n = W.shape
+    if fact is None:
+        fact = L.scaled_svd([W.cuda()], [None if scale32 is None else scale32.cuda()])
+        assert fact.status == 0
+    r = min(O.rank_for_ratio(m, n, ratio, rank_align), min(m, n))
+    sd = torch.ones(n, dtype=torch.float64) if scale32 is None else scale32.double()
+    Wd = W.double()
+    U, S, Vh = torch.linalg.svd(Wd * sd, full_matrices=False)
+    sig = fact.sigma(b).cpu().double()
+    assert sig.shape[0] == min(m, n)
+    assert torch.all(sig[:-1] >= sig[1:]), "sigma not sorted"
+    # 1e-4 relative on every kept sigma, above the fp32 noise floor of the oracle itself (LAPACK fp32
+    # has absolute error ~eps*sigma_max, so singular values below 1e-2*sigma_max get an absolute allowance)
+    rel = ((sig[:r] - S[:r]).abs() / (S[:r] + 1e-2 * S[0])).max().item() * (1 + 1e-2)
+    rel = max(rel, ((sig[:r] - S[:r]).abs() / S[:r])[S[:r] > 1e-2 * S[0]].max().item())
+    assert rel < SIGMA_RTOL, f"sigma rel err {rel}"
+    A, B = fact.extract(r, fuse, out_dtype, b)
+    assert A.shape == (m, r) and B.shape == (r, n) and A.dtype == out_dtype
+    A, B = A.cpu().double(), B.cpu().double()
+    Wtr = (U[:, :r] * S[:r]) @ Vh[:r] / sd
+    rec = _scaled_norm(A @ B - Wtr, sd) / _scaled_norm(Wd, sd)
+    tol = RECON_TOL if out_dtype == torch.float32 else 2 * RECON_TOL
+    assert rec < tol, f"reconstruction vs exact truncation {rec}"
+    # balance of the fusion: column norms of A are sigma^a
+    a_exp = {"UV": 0.5, "U": 1.0, "V": 0.0}[fuse]
+    if out_dtype == torch.float32:
+        an = A.norm(dim=0)
+        assert torch.allclose(an, S[:r] ** a_exp, rtol=2e-4, atol=1e-7)
+    return fact, rel, rec
+
+
+def test_golden_cases_exact_parity(golden_cases):
+    """Every upstream-generated case: our factors vs the exact-SVD oracle and vs the upstream result."""
+    L = _lib()
+    for c in golden_cases:
+        s = None
+        if c["act_aware"]:
+            s = L.scaling_vector(c["sdm"].cuda(), None if c["fisher"] is None else c["fisher"].cuda(), c["alpha"], c["n"], "cuda").cpu()
+            want = O.scaling_vector(c["sdm"], c["fisher"], c["alpha"]).float()
+            assert torch.allclose(s, want, rtol=2e-3 if c["sdm"].dtype == torch.float16 else 1e-6, atol=0)
+        fact, _, _ = check_factorisation(c["W"], s, c["ratio"], c["sigma_fuse"], torch.float32, c["rank_align"])
+        # ours (exact) must reconstruct the scaled weight at least as well as upstream's svd_lowrank result
+        r = c["truncation_rank"]
+        A, B = fact.extract(r, c["sigma_fuse"], torch.float32)
+        sd = torch.ones(c["n"], dtype=torch.float64) if s is None else s.double()
+        Wd = c["W"].double()
+        ours = _scaled_norm(A.cpu().double() @ B.cpu().double() - Wd, sd)
+        ref = _scaled_norm(c["A"].double() @ c["B"].double() - Wd, sd)
+        assert ours <= ref * (1 + 1e-4) + 2e-3 * _scaled_norm(Wd, sd) * (c["W"].dtype == torch.float16)
+
+
+def test_from_linear_module_surface(golden_cases):
+    from asvd4llm_b200 import SVDLinear
+    for c in golden_cases[::3]:
+        lin = nn.Linear(c["n"], c["m"], bias=c["bias"] is not None)
+        lin.weight.data = c["W"].clone()
+        if c["bias"] is not None:
+            lin.bias.data = c["bias"].clone()
+        lin = lin.cuda()
+        lin.scaling_diag_matrix = c["sdm"].cuda()
+        if c["fisher"] is not None:
+            lin.fisher_info = c["fisher"].cuda()
+        w_before = lin.weight.data.clone()
+        mod = SVDLinear.from_linear(lin, c["ratio"], act_aware=c["act_aware"], alpha=c["alpha"], sigma_fuse=c["sigma_fuse"],
+                                    rank_align=c["rank_align"])
+        assert isinstance(mod, SVDLinear)
+        assert list(mod.state_dict().keys()) == c["state_dict_keys"]
+        assert mod.truncation_rank == c["truncation_rank"]
+        assert mod.ALinear.weight.dtype == c["W"].dtype and mod.ALinear.weight.shape == c["A"].shape
+        assert mod.BLinear.weight.shape == c["B"].shape
+        assert torch.equal(lin.weight.data, w_before), "from_linear must not mutate the layer"
+        if c["bias"] is not None:
+            assert mod.ALinear.bias.data_ptr() == lin.bias.data_ptr()
+        x = c["x"].cuda()
+        y = mod(x)
+        yref = O.lowrank_forward(c["x"], mod.ALinear.weight.data.cpu(), mod.BLinear.weight.data.cpu(),
+                                 None if c["bias"] is None else c["bias"], compute_dtype=torch.float64)
+        tol = 2e-3 * max(1.0, yref.abs().max().item()) if c["W"].dtype == torch.float16 else 1e-4
+        assert (y.cpu().double() - yref).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("m,n,kind", [(1024, 1024, "gauss"), (1024, 1024, "power"), (1536, 512, "gauss"), (512, 1536, "power"),
+                                      (300, 700, "gauss"), (129, 257, "gauss")])
+def test_synthetic_sigma_and_reconstruction(m, n, kind):
+    W, s = O.synthetic_weight(m, n, seed=233, kind=kind)
+    scale = (s ** 0.5 + 1e-6).float()
+    for fuse in ("UV", "U", "V"):
+        check_factorisation(W, scale, 0.9, fuse)
+
+
+def test_batched_equals_single_bitwise():
+    """Sharding invariant: a weight's factors do not depend on what else is in the launch."""
+    L = _lib()
+    Ws, Ss = [], []
+    for b in range(3):
+        W, s = O.synthetic_weight(512, 384, seed=10 + b)
+        Ws.append(W.cuda()); Ss.append((s ** 0.5 + 1e-6).float().cuda())
+    batched = L.scaled_svd(Ws, Ss)
+    for b in range(3):
+        single = L.scaled_svd([Ws[b]], [Ss[b]])
+        assert torch.equal(single.sigma(0), batched.sigma(b))
+        A1, B1 = single.extract(200, "UV", torch.float16, 0)
+        A2, B2 = batched.extract(200, "UV", torch.float16, b)
+        assert torch.equal(A1, A2) and torch.equal(B1, B2)
+
+
+def test_edge_cases():
+    L = _lib()
+    # rank-deficient weight and exact-zero scale channels
+    g = torch.Generator().manual_seed(5)
+    W = (torch.randn(200, 40, generator=g) @ torch.randn(40, 160, generator=g) * 0.01).half()
+    sdm = torch.rand(160, generator=g).half(); sdm[::5] = 0
+    s = L.scaling_vector(sdm.cuda(), None, 0.5, 160, "cuda")
+    assert torch.allclose(s.cpu(), O.scaling_vector(sdm, None, 0.5).float(), rtol=2e-3)
+    fact = L.scaled_svd([W.cuda()], [s])
+    A, B = fact.extract(100, "UV", torch.float32)
+    assert torch.isfinite(A).all() and torch.isfinite(B).all()
+    sd = s.cpu().double()
+    rec = _scaled_norm(A.cpu().double() @ B.cpu().double() - W.double(), sd) / _scaled_norm(W.double(), sd)
+    assert rec < 2e-3            # rank 40 < 100: exact up to the fp16 rounding of W's low-rank structure
+    # all-zero weight
+    fact = L.scaled_svd([torch.zeros(64, 96, dtype=torch.half, device="cuda")], [None])
+    A, B = fact.extract(30, "UV", torch.float16)
+    assert (A == 0).all() and (B == 0).all() and (fact.sigma() == 0).all()
+    # NaN -> status 4 -> module-level fallback like upstream (fresh nn.Linear, "nan in S")
+    from asvd4llm_b200 import SVDLinear
+    lin = nn.Linear(64, 48).half().cuda()
+    lin.weight.data[3, 5] = float("nan")
+    out = SVDLinear.from_linear(lin, 0.9)
+    assert isinstance(out, nn.Linear) and out.weight.shape == lin.weight.shape and out.weight.dtype == torch.float16
+    # act_aware without statistics raises like upstream
+    lin2 = nn.Linear(64, 48).cuda()
+    with pytest.raises(AttributeError):
+        SVDLinear.from_linear(lin2, 0.9, act_aware=True)
+    # requested rank above min(m, n) yields min(m, n) and an exact reconstruction (quirk 6)
+    lin3 = nn.Linear(96, 32).cuda()
+    mod = SVDLinear.from_linear(lin3, 1.9)
+    assert mod.truncation_rank == 32
+    rec = (mod.ALinear.weight.data @ mod.BLinear.weight.data - lin3.weight.data).norm() / lin3.weight.data.norm()
+    assert rec < 1e-5
+
+
+def test_sensitivity_cache_reuses_one_svd():
+    from asvd4llm_b200 import SVDLinear, _lib as L
+    W, s = O.synthetic_weight(256, 256, seed=3)
+    lin = nn.Linear(256, 256, bias=False)
+    lin.weight.data = W
+    lin = lin.cuda(); lin.scaling_diag_matrix = s.half().cuda()
+    before = L.profile_read()["gram"][1]
+    mods = [SVDLinear.from_linear(lin, r, act_aware=True, alpha=0.5) for r in O.RATIO_CANDIDATES]
+    mid = L.profile_read()["gram"][1]
+    assert mid > before
+    SVDLinear.from_linear(lin, 0.5, act_aware=True, alpha=0.5)
+    assert L.profile_read()["gram"][1] == mid, "second visit of the same layer must re-slice the cached SVD"
+    assert [m.truncation_rank for m in mods] == [O.rank_for_ratio(256, 256, r) for r in O.RATIO_CANDIDATES]
+    lin.weight.data.mul_(2.0)          # in-place change bumps the version -> new SVD
+    SVDLinear.from_linear(lin, 0.5, act_aware=True, alpha=0.5)
+    assert L.profile_read()["gram"][1] > mid
+
+
+@pytest.mark.parametrize("r", [256, 512])
+def test_forward_parity_fp16(r):
+    """config 4 shapes at reduced M: 1e-3 max-abs with |y| < 1, and error vs fp64 no worse than the reference's."""
+    L = _lib()
+    g = torch.Generator().manual_seed(233)
+    n = m = 4096
+    x = (torch.randn(2, 512, n, generator=g) * 0.125).half()
+    B = (torch.randn(r, n, generator=g) / n ** 0.5).half()
+    A = (torch.randn(m, r, generator=g) / r ** 0.5 * 0.5).half()
+    bias = (torch.randn(m, generator=g) * 0.1).half()
+    for bi in (None, bias):
+        y = L.lowrank_forward(x.cuda(), A.cuda(), B.cuda(), None if bi is None else bi.cuda()).cpu()
+        y64 = O.lowrank_forward(x, A, B, bi, compute_dtype=torch.float64)
+        assert y64.abs().max() < 1.0
+        yref16 = O.lowrank_forward(x.float(), A.float(), B.float(), None if bi is None else bi.float())   # fp32 math of the same module
+        err = (y.double() - y64).abs().max().item()
+        assert err < 1e-3, err
+        assert (y.float() - yref16).abs().max().item() < 1e-3
+
+
+def test_forward_bf16_and_ragged_shapes():
+    L = _lib()
+    g = torch.Generator().manual_seed(1)
+    for (M, n, r, m) in [(1, 64, 8, 32), (37, 100, 13, 77), (130, 257, 129, 131)]:
+        x = torch.randn(M, n, generator=g).bfloat16(); B = (torch.randn(r, n, generator=g) / n ** 0.5).bfloat16()
+        A = (torch.randn(m, r, generator=g) / r ** 0.5).bfloat16()
+        y = L.lowrank_forward(x.cuda(), A.cuda(), B.cuda(), None).cpu()
+        t = (x.double() @ B.double().t()).bfloat16().double()
+        y64 = t @ A.double().t()
+        assert (y.double() - y64).abs().max().item() < 3e-2 * max(1.0, y64.abs().max().item())
+    y = L.lowrank_forward(torch.empty(0, 64, dtype=torch.half, device="cuda"), torch.randn(32, 8).half().cuda(),
+                          torch.randn(8, 64).half().cuda(), None)
+    assert y.shape == (0, 32)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("method", ["abs_mean", "abs_max"])
+def test_absstat_matches_hook_math(dtype, method):
+    L = _lib()
+    g = torch.Generator().manual_seed(9)
+    for (Lr, n) in [(2048, 768), (5, 3), (333, 1001)]:
+        acc = torch.zeros(n, dtype=dtype, device="cuda")
+        want = 0
+        for k in range(3):
+            x = (torch.randn(1, Lr, n, generator=g) * (k + 1)).to(dtype).cuda()
+            L.absstat_accum(x, acc, method)
+            want = O.abs_stat_update(want, x, method)
+        if method == "abs_max":
+            assert torch.equal(acc, want)
+        else:
+            ulp = {torch.float16: 1e-3, torch.bfloat16: 8e-3, torch.float32: 2e-6}[dtype]
+            assert torch.allclose(acc.float(), want.float(), rtol=2 * ulp, atol=0)
+
+
+def _args(**kw):
+    base = dict(scaling_method="abs_mean", alpha=0.5, n_calib_samples=3, calib_dataset="synthetic", compress_kv_cache=False,
+                rank_align=1, kv_cache_ratio_target=-1, param_ratio_target=0.8, ppl_target=-1, act_aware=True, sigma_fuse="UV")
+    base.update(kw)
+    return argparse.Namespace(**base)
+
+
+def test_tiny_opt_pipeline_against_upstream_golden(golden_pipeline, tmp_path, monkeypatch):
+    """calib -> sensitivity -> search -> decomposition on the tiny OPT, every stage against the upstream run."""
+    from asvd4llm_b200 import SVDLinear
+    from asvd4llm_b200.act_aware_utils import calib_input_distribution
+    from asvd4llm_b200.sensitivity import calib_sensitivity_ppl
+    from asvd4llm_b200.binary_search import binary_search_truncation_rank
+    from asvd4llm_b200.evaluate_utils import evaluate_perplexity
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("cache")
+    loader = golden_pipeline["loader"]
+    ids = torch.cat([b["input_ids"] for b in loader], 0)
+    for method in ("abs_max", "abs_mean"):
+        model = build_tiny_opt(golden_pipeline).cuda()
+        calib_input_distribution(model, loader, method, use_cache=False)
+        want = golden_pipeline[f"sdm_{method}"]
+        for name, mod in model.named_modules():
+            if isinstance(mod, nn.Linear):
+                assert torch.allclose(mod.scaling_diag_matrix.cpu(), want[name], rtol=1e-4, atol=1e-6), (method, name)
+        saved = torch.load(f"cache/synthetic_tiny-opt_calib_input_distribution_{method}.pt")
+        assert list(saved.keys()) == list(want.keys())
+    assert evaluate_perplexity(model, ids, 3) == pytest.approx(golden_pipeline["ppl_raw"], rel=1e-3)
+    with contextlib.redirect_stdout(io.StringIO()):
+        sens = calib_sensitivity_ppl(model, loader, _args(), use_cache=False)
+    want = golden_pipeline["sensitivity"]
+    assert list(sens.keys()) == list(want.keys())
+    for layer in want:
+        assert list(sens[layer].keys()) == list(want[layer].keys())
+        for ratio in want[layer]:
+            # exact truncation vs svd_lowrank: same table up to the truncation-quality difference
+            assert sens[layer][ratio] == pytest.approx(want[layer][ratio], rel=2e-2), (layer, ratio)
+    assert os.path.exists("cache/synthetic_tiny-opt_sensitivity_abs_mean_0.5_3_synthetic.pt")
+    # the search on the SAME table must make the same decisions
+    with contextlib.redirect_stdout(io.StringIO()):
+        binary_search_truncation_rank(model, want, loader, _args())
+    ranks = {n: m.truncation_rank for n, m in model.named_modules() if isinstance(m, SVDLinear)}
+    assert ranks == golden_pipeline["truncation_ranks"]
+    assert list(model.state_dict().keys()) == golden_pipeline["decomposed_state_dict_keys"]
+    ppl = evaluate_perplexity(model, ids, 3)
+    assert ppl <= golden_pipeline["ppl_decomposed"] * 1.01, (ppl, golden_pipeline["ppl_decomposed"])
+
+
+def test_full_size_4096_properties():
+    """configs[1] at full size: sigma vs LAPACK on the host, reconstruction vs the projector property."""
+    L = _lib()
+    W, s = O.synthetic_weight(4096, 4096, seed=233)
+    scale = (s ** 0.5 + 1e-6).float()
+    fact = L.scaled_svd([W.cuda()], [scale.cuda()])
+    assert fact.status == 0
+    r = O.rank_for_ratio(4096, 4096, 0.9)
+    assert r == 1843
+    ref = torch.linalg.svdvals(W.float() * scale)          # fp32 LAPACK: the north_star oracle
+    sig = fact.sigma().cpu()
+    assert ((sig[:r] - ref[:r]).abs() / ref[:r]).max().item() < SIGMA_RTOL
+    A, B = fact.extract(r, "UV", torch.float32)
+    # A B = P W with P an orthogonal projector of rank r: idempotence and energy identities, size independent
+    Wc = W.float().cuda()
+    AB = A @ B
+    An = A / A.norm(dim=0, keepdim=True)
+    gram_err = (An.t() @ An - torch.eye(r, device="cuda")).abs().max().item()
+    assert gram_err < 5e-5
+    assert ((An @ (An.t() @ Wc)) - AB).norm().item() / AB.norm().item() < 1e-4
+    sc = scale.cuda()
+    kept = ((AB * sc).norm() ** 2).item()
+    assert kept == pytest.approx((ref[:r].double() ** 2).sum().item(), rel=1e-4)
