@@ -1,0 +1,207 @@
+// tcgen05 GEMM for the low-rank forward (a7): C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]), 16-bit operands (both
+// K-major, as activations [tokens, features] and nn.Linear weights [out, in] are), fp32 accumulation in TMEM.
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0     TMA producer : 128 x 64 tile of A and BN x 64 tile of B per stage (128-byte swizzle), 4 stages
+//   warp 1     MMA issuer   : one elected thread issues 4 x tcgen05.mma (M=128, N=BN, K=16) per stage into one of
+//                             two TMEM accumulators; tcgen05.commit releases the stage / publishes the accumulator
+//   warp 2     TMEM allocator (2 x BN columns)
+//   warps 4-7  epilogue     : tcgen05.ld (32 lanes x 32 columns per warp and step) -> + bias -> 16-bit -> global,
+//                             overlapped with the next tile's MMAs through the second accumulator
+// SVDLinear.forward = two launches: t = x B^T, y = t A^T + b (the [tokens, r] intermediate stays L2-resident for
+// the sizes of BASELINE config 4: 64 Ki x 256 x 2 B = 32 MiB per 128 MiB L2).
+#include "common.cuh"
+#include "umma.cuh"
+#include <type_traits>
+
+namespace asvd {
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 64;            // 16-bit elements per stage row = 128 bytes = one swizzle atom
+constexpr int STAGES = 4;
+constexpr int GEMM_THREADS = 256;
+
+template <int BN> struct GemmSmem {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + tmem pointer + alignment slack
+};
+
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <typename T, int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, T* __restrict__ C,
+               int64_t ldc, const T* __restrict__ bias, int M, int N, int K) {
+  using S = GemmSmem<BN>;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;      // [2] accumulator ready
+  uint64_t* tempty = tfull + 2;          // [2] accumulator drained
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m0 = (t / num_n) * BM, n0 = (t % num_n) * BN;
+        for (int k = 0; k < num_k; ++k) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          unsigned char* a = smem + stage * S::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[stage], S::STAGE_BYTES);
+          tma_load_2d(a, &tmA, &full[stage], k * BK, m0);
+          tma_load_2d(a + S::A_BYTES, &tmB, &full[stage], k * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value ? 1 : 0, BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1);
+        mbar_wait(&tempty[buf], (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+        for (int k = 0; k < num_k; ++k) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint64_t adesc = make_desc_kmajor_sw128(a_addr);
+          const uint64_t bdesc = make_desc_kmajor_sw128(a_addr + S::A_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk)          // +32 bytes (>>4 = 2) per K=16 step inside the swizzle atom
+            mma_f16_ss(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) ? 1u : 0u);
+          tc_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;                              // TMEM lane quadrant of this warp
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      const int m0 = (t / num_n) * BM, n0 = (t % num_n) * BN;
+      mbar_wait(&tfull[buf], use & 1);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < M;
+      T* crow = C + (int64_t)row * ldc;
+      const bool vec_ok = ((ldc * (int64_t)sizeof(T)) % 16 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32), v);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (row_ok && col0 < N) {
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (col0 + j < N) f[j] += to_f32<T>(bias[col0 + j]);
+        }
+        if (vec_ok && col0 + 32 <= N) {
+          uint4* dst = reinterpret_cast<uint4*>(crow + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            dst[j] = make_uint4(pack2<T>(f[8 * j], f[8 * j + 1]), pack2<T>(f[8 * j + 2], f[8 * j + 3]),
+                                pack2<T>(f[8 * j + 4], f[8 * j + 5]), pack2<T>(f[8 * j + 6], f[8 * j + 7]));
+        } else {
+          for (int j = 0; j < 32 && col0 + j < N; ++j) crow[col0 + j] = from_f32<T>(f[j]);
+        }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 2 * BN);
+}
+
+template <typename T, int BN>
+static cudaError_t launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, T* C, int64_t ldc, const T* bias, int M, int N,
+                             int K, int sms, cudaStream_t st) {
+  using S = GemmSmem<BN>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<T, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  gemm_tn_kernel<T, BN><<<tiles < sms ? tiles : sms, GEMM_THREADS, S::TOTAL, st>>>(tmA, tmB, C, ldc, bias, M, N, K);
+  return cudaGetLastError();
+}
+
+// returns 0 on launch, 1 if the operands do not meet TMA's alignment rules (caller uses the SIMT kernel), <0 on error
+template <typename T>
+int gemm_tn_tc(const T* A, int64_t lda, const T* B, int64_t ldb, T* C, int64_t ldc, const T* bias, int M, int N, int K,
+               cudaStream_t st) {
+  auto ok = [](const void* p, int64_t ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld * 2) % 16 == 0; };
+  if (!ok(A, lda) || !ok(B, ldb) || K < 8) return 1;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const CUtensorMapDataType dt = std::is_same<T, __half>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUtensorMap tmA, tmB;
+  const int BN = (N > 128) ? 256 : 128;
+  if (!make_tmap_2d(&tmA, dt, 2, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK)) return -1;
+  if (!make_tmap_2d(&tmB, dt, 2, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)BN, BK)) return -1;
+  cudaError_t e = (BN == 256) ? launch_tn<T, 256>(tmA, tmB, C, ldc, bias, M, N, K, sms, st)
+                              : launch_tn<T, 128>(tmA, tmB, C, ldc, bias, M, N, K, sms, st);
+  return e == cudaSuccess ? 0 : -2;
+}
+
+template int gemm_tn_tc<__half>(const __half*, int64_t, const __half*, int64_t, __half*, int64_t, const __half*, int, int, int, cudaStream_t);
+template int gemm_tn_tc<__nv_bfloat16>(const __nv_bfloat16*, int64_t, const __nv_bfloat16*, int64_t, __nv_bfloat16*, int64_t,
+                                       const __nv_bfloat16*, int, int, int, cudaStream_t);
+
+}  // namespace tc
+}  // namespace asvd

@@ -2,6 +2,8 @@
 #include <float.h>
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tc.h"
+#include <type_traits>
 
 namespace asvd {
 
@@ -120,23 +122,31 @@ static int absstat_run(const void* x, int64_t ldx, int64_t L, int n, int mode, v
 }
 
 template <typename T>
+static int forward_gemm(const T* A, int64_t lda, const T* B, int64_t ldb, T* C, int64_t ldc, const T* bias, int M, int N, int K,
+                        cudaStream_t st) {
+  prof_begin(K_FORWARD, st);
+  int rc = 1;
+  if constexpr (!std::is_same<T, float>::value) rc = tc::gemm_tn_tc<T>(A, lda, B, ldb, C, ldc, bias, M, N, K, st);
+  if (rc == 1) {   // operands not TMA-eligible (unaligned rows): same contraction on the SIMT kernel
+    GemmBatch gb;
+    memset(&gb, 0, sizeof(gb));
+    cudaError_t e = launch_gemm128<T, T, T, false>(A, lda, B, ldb, C, ldc, M, N, K, nullptr, nullptr, bias, 1, gb, st);
+    rc = (e == cudaSuccess) ? 0 : -2;
+  }
+  prof_end(K_FORWARD, st);
+  if (rc != 0) { set_error("forward GEMM launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return ASVD_ERR_CUDA; }
+  return ASVD_OK;
+}
+
+template <typename T>
 static int forward_run(const void* x, int64_t ldx, int64_t M, int n, const void* B, int64_t ldb, int r, const void* A,
                        int64_t lda, int m, const void* bias, void* y, int64_t ldy, void* scratch, cudaStream_t st) {
-  GemmBatch gb;
-  memset(&gb, 0, sizeof(gb));
   T* t = reinterpret_cast<T*>(scratch);
   // t[M, r] = x B^T  (materialised in the module dtype, as upstream's BLinear output is)
-  prof_begin(K_FORWARD, st);
-  cudaError_t e = launch_gemm128<T, T, T, false>((const T*)x, ldx, (const T*)B, ldb, t, r, (int)M, r, n, nullptr, nullptr,
-                                                 (const T*)nullptr, 1, gb, st);
-  prof_end(K_FORWARD, st);
-  ASVD_CUDA_CHECK(e);
-  prof_begin(K_FORWARD, st);
+  int rc = forward_gemm<T>((const T*)x, ldx, (const T*)B, ldb, t, r, (const T*)nullptr, (int)M, r, n, st);
+  if (rc) return rc;
   // y[M, m] = t A^T + bias
-  e = launch_gemm128<T, T, T, false>(t, r, (const T*)A, lda, (T*)y, ldy, (int)M, m, r, nullptr, nullptr, (const T*)bias, 1, gb, st);
-  prof_end(K_FORWARD, st);
-  ASVD_CUDA_CHECK(e);
-  return ASVD_OK;
+  return forward_gemm<T>(t, r, (const T*)A, lda, (T*)y, ldy, (const T*)bias, (int)M, m, r, st);
 }
 
 extern "C" {

@@ -21,6 +21,8 @@
 #include <utility>
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "svd_tc.h"
+#include <stdlib.h>
 
 namespace asvd {
 
@@ -251,7 +253,7 @@ __device__ __forceinline__ float2 jacobi_cs(float app, float aqq, float apq) {
 __global__ void __launch_bounds__(SOLVE_THREADS, 1)
 solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, float* __restrict__ Rout,
              int* __restrict__ pairflag, unsigned* __restrict__ maxoff_bits, int* __restrict__ status,
-             const int* __restrict__ done, float tol) {
+             const int* __restrict__ done, float tol, int transpose_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* G = reinterpret_cast<float*>(smem_raw);            // [JK][SLD]; later E = R^T R
   float* Rs = G + JK * SLD;                                 // [JK][SLD]; R in sorted column order (after the sweep)
@@ -449,9 +451,14 @@ solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, flo
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float4 rr = *reinterpret_cast<const float4*>(&Rs[(ta * 4 + i) * SLD + tb * 4]);
-      *reinterpret_cast<float4*>(&Ro[(ta * 4 + i) * JK + tb * 4]) =
-          make_float4(1.5f * rr.x - 0.5f * o[i][0], 1.5f * rr.y - 0.5f * o[i][1], 1.5f * rr.z - 0.5f * o[i][2],
-                      1.5f * rr.w - 0.5f * o[i][3]);
+      const float4 w = make_float4(1.5f * rr.x - 0.5f * o[i][0], 1.5f * rr.y - 0.5f * o[i][1], 1.5f * rr.z - 0.5f * o[i][2],
+                                   1.5f * rr.w - 0.5f * o[i][3]);
+      if (!transpose_out) {
+        *reinterpret_cast<float4*>(&Ro[(ta * 4 + i) * JK + tb * 4]) = w;
+      } else {                      // R^T for the tensor-core update (A operand, K-major)
+        Ro[(tb * 4 + 0) * JK + ta * 4 + i] = w.x; Ro[(tb * 4 + 1) * JK + ta * 4 + i] = w.y;
+        Ro[(tb * 4 + 2) * JK + ta * 4 + i] = w.z; Ro[(tb * 4 + 3) * JK + ta * 4 + i] = w.w;
+      }
     }
   }
 }
@@ -710,6 +717,17 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
     ASVD_LAUNCH(K_PREP, st, (prep_kernel<T><<<grid, 256, 0, st>>>(d_W, scale, ldw, p.m, p.n, p.tall, X, xs, p.len_pad)));
     ASVD_CUDA_CHECK(cudaGetLastError());
   }
+  // ASVD_B200_SIMT=1 selects the fp32 SIMT Gram / update kernels (kept as the in-library reference the
+  // tensor-core kernels are tested against); default is the tcgen05 path.
+  const char* simt_env = getenv("ASVD_B200_SIMT");
+  const bool use_tc = !(simt_env && simt_env[0] == '1');
+  CUtensorMap tmK, tmMN;
+  if (use_tc) {
+    if (!tc::make_x_tmap(&tmK, X, p.batch, p.nv_pad, p.len_pad) || !tc::make_x_tmap_mn(&tmMN, X, p.batch, p.nv_pad, p.len_pad)) {
+      set_error("cuTensorMapEncodeTiled failed");
+      return ASVD_ERR_CUDA;
+    }
+  }
   std::vector<unsigned> h_maxoff(p.batch);
   std::vector<int> h_done(p.batch, 0), h_sweeps(p.batch, 0);
   int sweep = 0;
@@ -718,10 +736,18 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
     ASVD_CUDA_CHECK(cudaMemsetAsync(maxoff, 0, sizeof(unsigned) * p.batch, st));
     for (int r = 0; r < p.rounds; ++r) {
       const int2* pr = d_pairs + (size_t)r * p.pairs;
-      ASVD_LAUNCH(K_GRAM, st, (gram_kernel<<<dim3(p.chunks, p.pairs, p.batch), 256, 0, st>>>(X, xs, p.len_pad, pr, p.len_pad, p.chunks, p.pairs, G, done)));
-      ASVD_LAUNCH(K_SOLVE, st, (solve_kernel<<<dim3(p.pairs, p.batch), SOLVE_THREADS, SOLVE_SMEM, st>>>(G, p.chunks, p.pairs, R, flag, maxoff, status, done, tol)));
-      const int ctas_x = (p.len_pad / 128 + UPD_TILES - 1) / UPD_TILES;
-      ASVD_LAUNCH(K_UPDATE, st, (update_kernel<<<dim3(ctas_x, p.pairs, p.batch), 256, UPDATE_SMEM, st>>>(X, xs, p.len_pad, pr, p.len_pad, p.pairs, R, flag, done)));
+      if (use_tc) {
+        ASVD_LAUNCH(K_GRAM, st, ASVD_CUDA_CHECK(tc::launch_gram_tc(tmK, pr, p.pairs, p.chunks, GRAM_CHUNK, p.len_pad, p.nv_pad, p.batch, G, done, st)));
+      } else {
+        ASVD_LAUNCH(K_GRAM, st, (gram_kernel<<<dim3(p.chunks, p.pairs, p.batch), 256, 0, st>>>(X, xs, p.len_pad, pr, p.len_pad, p.chunks, p.pairs, G, done)));
+      }
+      ASVD_LAUNCH(K_SOLVE, st, (solve_kernel<<<dim3(p.pairs, p.batch), SOLVE_THREADS, SOLVE_SMEM, st>>>(G, p.chunks, p.pairs, R, flag, maxoff, status, done, tol, use_tc ? 1 : 0)));
+      if (use_tc) {
+        ASVD_LAUNCH(K_UPDATE, st, ASVD_CUDA_CHECK(tc::launch_update_tc(tmMN, X, xs, p.len_pad, pr, p.pairs, p.nv_pad, p.len_pad, p.batch, R, flag, done, st)));
+      } else {
+        const int ctas_x = (p.len_pad / 128 + UPD_TILES - 1) / UPD_TILES;
+        ASVD_LAUNCH(K_UPDATE, st, (update_kernel<<<dim3(ctas_x, p.pairs, p.batch), 256, UPDATE_SMEM, st>>>(X, xs, p.len_pad, pr, p.len_pad, p.pairs, R, flag, done)));
+      }
     }
     ASVD_CUDA_CHECK(cudaGetLastError());
     ASVD_CUDA_CHECK(cudaMemcpyAsync(h_maxoff.data(), maxoff, sizeof(unsigned) * p.batch, cudaMemcpyDeviceToHost, st));

@@ -1,0 +1,400 @@
+// Tensor-core (tcgen05, kind::tf32) bodies of the two streaming passes of the block-Jacobi SVD.
+//
+// fp32 accuracy on a TF32 pipe: every fp32 operand x is split as x = hi + lo with hi = rna_tf32(x) (exactly
+// representable, so the MMA's internal truncation is a no-op) and lo = x - hi (|lo| <= 2^-11 |x|); a product is
+// accumulated as hi*hi + lo*hi + hi*lo in the fp32 TMEM accumulator, dropping only the 2^-22 lo*lo term.  The
+// split is done in shared memory by dedicated warps between the TMA landing and the MMA issue.
+//
+// gram_tc_kernel: G_c = P_c P_c^T for the 128-vector panel of a block pair over a chunk of columns.  Both MMA
+// operands are the SAME K-major tile (vectors are rows of X, the contraction runs along the contiguous dimension).
+//   warp 0  TMA producer (two 64-row boxes per stage: block I rows, block J rows), 128-byte swizzle, 4 stages
+//   warp 1  MMA issuer: 4 K-steps x 3 split terms of tcgen05.mma M=128 N=128 K=8 per stage
+//   warp 2  TMEM allocator (2 accumulators x 128 columns)
+//   warps 4-7  epilogue: tcgen05.ld -> global partial Gram
+//   warps 8-11 split: hi/lo rewrite of the landed tile, fence.proxy.async, arrive
+#include <type_traits>
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace asvd {
+namespace tc {
+
+constexpr int GR_STAGES = 4;
+constexpr int GR_HI_BYTES = 128 * 128;           // 128 rows x 32 floats
+constexpr int GR_STAGE_BYTES = 2 * GR_HI_BYTES;  // hi + lo
+constexpr int GR_BAR_OFFSET = GR_STAGES * GR_STAGE_BYTES;
+constexpr int GR_SMEM = GR_BAR_OFFSET + 256 + 1024;
+constexpr int GR_THREADS = 384;
+
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// in-place hi/lo split of a 16 KB tile by 128 threads (layout-agnostic: same offsets in both tiles)
+__device__ __forceinline__ void split_tile(float4* hi, float4* lo, int t) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float4 v = hi[t + 128 * j];
+    float4 h = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
+    hi[t + 128 * j] = h;
+    lo[t + 128 * j] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+  }
+}
+
+__global__ void __launch_bounds__(GR_THREADS, 1)
+gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__ pairs, int pairs_per_mat, int chunks,
+               int chunk_cols, int len_pad, int nv_pad, int n_items, float* __restrict__ Gpart,
+               const int* __restrict__ done) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + GR_BAR_OFFSET);
+  uint64_t* split_done = full + GR_STAGES;
+  uint64_t* empty = split_done + GR_STAGES;
+  uint64_t* tfull = empty + GR_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmX);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < GR_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&split_done[i], 4); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int per_mat = pairs_per_mat * chunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int b = item / per_mat, p = (item % per_mat) / chunks, c = item % chunks;
+        if (done[b]) continue;
+        const int2 pr = pairs[p];
+        const int k0 = c * chunk_cols, k1 = min(len_pad, k0 + chunk_cols);
+        for (int k = k0; k < k1; k += 32) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          unsigned char* hi = smem + stage * GR_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[stage], GR_HI_BYTES);
+          tma_load_2d(hi, &tmX, &full[stage], k, b * nv_pad + pr.x * JB);
+          tma_load_2d(hi + GR_HI_BYTES / 2, &tmX, &full[stage], k, b * nv_pad + pr.y * JB);
+          if (++stage == GR_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(2, 128, 128);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int b = item / per_mat, c = item % chunks;
+        if (done[b]) continue;
+        const int buf = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1);
+        ++it;
+        mbar_wait(&tempty[buf], (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
+        const int k0 = c * chunk_cols, k1 = min(len_pad, k0 + chunk_cols);
+        uint32_t acc = 0;
+        for (int k = k0; k < k1; k += 32) {
+          mbar_wait(&split_done[stage], phase);
+          tc_fence_after();
+          const uint32_t hi_addr = smem_u32(smem + stage * GR_STAGE_BYTES);
+          const uint64_t dh = make_desc_kmajor_sw128(hi_addr), dl = make_desc_kmajor_sw128(hi_addr + GR_HI_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {              // K = 8 tf32 = 32 bytes per step
+            const uint64_t o = (uint64_t)(kk * 2);
+            mma_tf32_ss(d_tmem, dh + o, dh + o, idesc, acc);
+            acc = 1;
+            mma_tf32_ss(d_tmem, dl + o, dh + o, idesc, 1u);
+            mma_tf32_ss(d_tmem, dh + o, dl + o, idesc, 1u);
+          }
+          tc_commit(&empty[stage]);
+          if (++stage == GR_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull[buf]);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    const int q = warp - 4;
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int b = item / per_mat;
+      if (done[b]) continue;
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      ++it;
+      mbar_wait(&tfull[buf], use & 1);
+      tc_fence_after();
+      float* G = Gpart + (int64_t)item * (JK * JK) + (q * 32 + lane) * JK;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + c * 32), v);
+        tmem_ld_wait();
+        float4* dst = reinterpret_cast<float4*>(G + c * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                               __uint_as_float(v[4 * j + 3]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+    }
+  } else if (warp >= 8) {
+    const int t = threadIdx.x - 256;
+    int stage = 0; uint32_t phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int b = item / per_mat, c = item % chunks;
+      if (done[b]) continue;
+      const int k0 = c * chunk_cols, k1 = min(len_pad, k0 + chunk_cols);
+      for (int k = k0; k < k1; k += 32) {
+        mbar_wait(&full[stage], phase);
+        float4* hi = reinterpret_cast<float4*>(smem + stage * GR_STAGE_BYTES);
+        split_tile(hi, hi + GR_HI_BYTES / 16, t);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split_done[stage]);
+        if (++stage == GR_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 256);
+}
+
+// ------------------------------------------------------------------------------------------------ update
+// update_tc_kernel: panel <- R^T panel for one block pair and a run of 64-column tiles:
+//   D[j][c] = sum_i Rt[j][i] X[i][c]     M = 128 (j), N = 64 (c), K = 128 (i)
+// A = R^T (hi and lo halves) is written ONCE per CTA into tensor memory (tcgen05.st) and read from there by every
+// MMA; B = the X tile exactly as it lies in HBM (rows i, columns c contiguous: an MN-major operand), landed by TMA
+// with the 128B/32B-atom swizzle and split into hi/lo in place.  D goes back over the same rows of X.
+constexpr int UP_STAGES = 3;
+constexpr int UP_TN = 64;                          // columns per tile
+constexpr int UP_HI_BYTES = 128 * UP_TN * 4;       // 32 KB: two boxes of 128 rows x 32 floats
+constexpr int UP_STAGE_BYTES = 2 * UP_HI_BYTES;
+constexpr int UP_BAR_OFFSET = UP_STAGES * UP_STAGE_BYTES;
+constexpr int UP_SMEM = UP_BAR_OFFSET + 256 + 1024;
+constexpr int UP_THREADS = 384;
+constexpr uint32_t UP_TMEM_A_HI = 256, UP_TMEM_A_LO = 384;   // column offsets; D buffers at 0 and 64
+
+__global__ void __launch_bounds__(UP_THREADS, 1)
+update_tc_kernel(const __grid_constant__ CUtensorMap tmX, float* __restrict__ X, int64_t mat_stride, int ldx,
+                 const int2* __restrict__ pairs, int pairs_per_mat, int nv_pad, int tiles_total, int tiles_per_cta,
+                 const float* __restrict__ Rt, const int* __restrict__ pairflag, const int* __restrict__ done) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + UP_BAR_OFFSET);
+  uint64_t* split_done = full + UP_STAGES;
+  uint64_t* empty = split_done + UP_STAGES;
+  uint64_t* tfull = empty + UP_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* a_ready = tempty + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_ready + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int b = blockIdx.z, p = blockIdx.y;
+  if (done[b]) return;
+  const int idx = b * pairs_per_mat + p;
+  if (!pairflag[idx]) return;
+  const int2 pr = pairs[p];
+  const int tile0 = blockIdx.x * tiles_per_cta;
+  const int ntiles = min(tiles_per_cta, tiles_total - tile0);
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmX);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < UP_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&split_done[i], 4); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    mbar_init(a_ready, 4);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const int c0 = (tile0 + t) * UP_TN;
+        mbar_wait(&empty[stage], phase ^ 1);
+        unsigned char* hi = smem + stage * UP_STAGE_BYTES;
+        mbar_arrive_expect_tx(&full[stage], UP_HI_BYTES);
+        // box = 64 rows x 32 floats; rows 0-63 of the tile are block I, rows 64-127 block J; two 32-column groups
+        for (int g = 0; g < 2; ++g) {
+          tma_load_2d(hi + g * 16384, &tmX, &full[stage], c0 + g * 32, b * nv_pad + pr.x * JB);
+          tma_load_2d(hi + g * 16384 + 8192, &tmX, &full[stage], c0 + g * 32, b * nv_pad + pr.y * JB);
+        }
+        if (++stage == UP_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(2, 128, UP_TN) | (1u << 16);     // B operand MN-major
+      mbar_wait(a_ready, 0);
+      tc_fence_after();
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        const uint32_t use = (uint32_t)(t >> 1);
+        mbar_wait(&tempty[buf], (use & 1) ^ 1);
+        mbar_wait(&split_done[stage], phase);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * UP_TN);
+        const uint32_t hi_addr = smem_u32(smem + stage * UP_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {                    // K = 8 rows of the tile per step = 1024 bytes
+          const uint64_t bh = make_desc_mnmajor_sw128_32b(hi_addr + k * 1024, 16384);
+          const uint64_t bl = make_desc_mnmajor_sw128_32b(hi_addr + UP_HI_BYTES + k * 1024, 16384);
+          mma_tf32_ts(d_tmem, tmem_base + UP_TMEM_A_HI + k * 8, bh, idesc, k ? 1u : 0u);
+          mma_tf32_ts(d_tmem, tmem_base + UP_TMEM_A_LO + k * 8, bh, idesc, 1u);
+          mma_tf32_ts(d_tmem, tmem_base + UP_TMEM_A_HI + k * 8, bl, idesc, 1u);
+        }
+        tc_commit(&empty[stage]);
+        tc_commit(&tfull[buf]);
+        if (++stage == UP_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    const int q = warp - 4;
+    const int j = q * 32 + lane;                           // output vector of this thread = TMEM lane
+    {   // A = R^T: row j of Rt -> hi/lo -> tensor memory columns [256,384) and [384,512)
+      const float4* src = reinterpret_cast<const float4*>(Rt + (int64_t)idx * (JK * JK) + j * JK);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t h[32], l[32];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float4 v = src[c * 8 + e];
+          float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float hh = rna_tf32(x[i]);
+            h[e * 4 + i] = __float_as_uint(hh);
+            l[e * 4 + i] = __float_as_uint(x[i] - hh);
+          }
+        }
+        tmem_st_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + UP_TMEM_A_HI + c * 32, h);
+        tmem_st_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + UP_TMEM_A_LO + c * 32, l);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+    }
+    const int vec = (j < JB) ? pr.x * JB + j : pr.y * JB + (j - JB);
+    float* xrow = X + b * mat_stride + (int64_t)vec * ldx;
+    for (int t = 0; t < ntiles; ++t) {
+      const int buf = t & 1;
+      const uint32_t use = (uint32_t)(t >> 1);
+      mbar_wait(&tfull[buf], use & 1);
+      tc_fence_after();
+      const int c0 = (tile0 + t) * UP_TN;
+#pragma unroll
+      for (int c = 0; c < UP_TN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * UP_TN + c * 32), v);
+        tmem_ld_wait();
+        float4* dst = reinterpret_cast<float4*>(xrow + c0 + c * 32);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          dst[e] = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]),
+                               __uint_as_float(v[4 * e + 3]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+    }
+  } else if (warp >= 8) {
+    const int t128 = threadIdx.x - 256;
+    int stage = 0; uint32_t phase = 0;
+    for (int t = 0; t < ntiles; ++t) {
+      mbar_wait(&full[stage], phase);
+      float4* hi = reinterpret_cast<float4*>(smem + stage * UP_STAGE_BYTES);
+      split_tile(hi, hi + UP_HI_BYTES / 16, t128);
+      split_tile(hi + 1024, hi + UP_HI_BYTES / 16 + 1024, t128);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&split_done[stage]);
+      if (++stage == UP_STAGES) { stage = 0; phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static int g_sms = 0;
+static int sm_count() {
+  if (!g_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return g_sms;
+}
+
+// tensor map over X of the whole batch: [batch * nv_pad rows, len_pad cols] fp32, box 64 rows x 32 floats
+bool make_x_tmap(CUtensorMap* map, const float* X, int batch, int nv_pad, int len_pad) {
+  return make_tmap_2d(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, X, (uint64_t)batch * nv_pad, (uint64_t)len_pad, (uint64_t)len_pad,
+                      64, 32);
+}
+
+cudaError_t launch_gram_tc(const CUtensorMap& tmX, const int2* pairs, int pairs_per_mat, int chunks, int chunk_cols,
+                           int len_pad, int nv_pad, int batch, float* Gpart, const int* done, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  const int n_items = batch * pairs_per_mat * chunks;
+  const int grid = n_items < sm_count() ? n_items : sm_count();
+  gram_tc_kernel<<<grid, GR_THREADS, GR_SMEM, st>>>(tmX, pairs, pairs_per_mat, chunks, chunk_cols, len_pad, nv_pad, n_items,
+                                                    Gpart, done);
+  return cudaGetLastError();
+}
+
+
+// tensor map for the update: same matrix, box 64 rows x 32 floats, 128B swizzle with 32-byte atoms (MN-major operand)
+bool make_x_tmap_mn(CUtensorMap* map, const float* X, int batch, int nv_pad, int len_pad) {
+  return make_tmap_2d(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, X, (uint64_t)batch * nv_pad, (uint64_t)len_pad, (uint64_t)len_pad,
+                      64, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+}
+
+cudaError_t launch_update_tc(const CUtensorMap& tmX, float* X, int64_t mat_stride, int ldx, const int2* pairs,
+                             int pairs_per_mat, int nv_pad, int len_pad, int batch, const float* Rt, const int* pairflag,
+                             const int* done, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UP_SMEM);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  const int tiles_total = len_pad / UP_TN;
+  // aim for ~3 waves of CTAs so the one-off R^T load into tensor memory is amortised over >= 8 tiles
+  int ctas_x = (3 * sm_count() + pairs_per_mat * batch - 1) / (pairs_per_mat * batch);
+  int tiles_per_cta = (tiles_total + ctas_x - 1) / ctas_x;
+  if (tiles_per_cta < 8) tiles_per_cta = tiles_total < 8 ? tiles_total : 8;
+  ctas_x = (tiles_total + tiles_per_cta - 1) / tiles_per_cta;
+  update_tc_kernel<<<dim3(ctas_x, pairs_per_mat, batch), UP_THREADS, UP_SMEM, st>>>(tmX, X, mat_stride, ldx, pairs, pairs_per_mat,
+                                                                                  nv_pad, tiles_total, tiles_per_cta, Rt,
+                                                                                  pairflag, done);
+  return cudaGetLastError();
+}
+
+}  // namespace tc
+}  // namespace asvd

@@ -1,0 +1,93 @@
+"""N>1 host logic on CPU: world_size-2 gloo processes.  The kernels are not involved: the test
+drives the exchange steps with factors produced by the oracle."""
+import os, socket
+import pytest, torch, torch.nn as nn
+import torch.distributed as dist
+import torch.multiprocessing as mp
+from conftest import GOLDEN
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def test_lpt_partition_balances_llama_shapes():
+    from asvd4llm_b200.sharding import lpt_partition, layer_cost
+    costs = {}
+    for l in range(32):
+        for nme in ("q", "k", "v", "o"):
+            costs[f"l{l}.{nme}"] = layer_cost(4096, 4096)
+        costs[f"l{l}.gate"] = layer_cost(11008, 4096); costs[f"l{l}.up"] = layer_cost(11008, 4096)
+        costs[f"l{l}.down"] = layer_cost(4096, 11008)
+    costs["lm_head"] = layer_cost(32000, 4096)
+    for world in (1, 2, 4, 8):
+        shards = lpt_partition(costs, world)
+        assert sorted(sum(shards, [])) == sorted(costs)            # a partition
+        loads = [sum(costs[n] for n in s) for s in shards]
+        assert max(loads) / (sum(loads) / world) < 1.02            # SURVEY: 1.001 / 1.005 / 1.009
+    assert lpt_partition(costs, 4) == lpt_partition(costs, 4)      # deterministic
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from conftest import build_tiny_opt
+        from asvd4llm_b200 import SVDLinear
+        from asvd4llm_b200 import sharding
+        from asvd4llm_b200.sensitivity import enumerate_linears
+        from oracle import asvd_oracle as O
+        pipe = torch.load(os.path.join(GOLDEN, "tiny_opt_pipeline.pt"), weights_only=False)
+        model = build_tiny_opt(pipe)
+        owners = sharding.owner_map(model, world)
+        # calibration: each rank saw half of the samples -> SUM / MAX must equal the full statistic
+        for method in ("abs_mean", "abs_max"):
+            m2 = build_tiny_opt(pipe)
+            O.calib_input_distribution(m2, pipe["loader"][rank::world], method)
+            sharding.allreduce_calibration(m2, method)
+            for name, mod in m2.named_modules():
+                if isinstance(mod, nn.Linear):
+                    assert torch.allclose(mod.scaling_diag_matrix, pipe[f"sdm_{method}"][name], rtol=1e-5, atol=1e-7), (method, name)
+        # sensitivity: each rank holds the rows of its own layers
+        full = pipe["sensitivity"]
+        shard = {k: v for k, v in full.items() if owners[k] == rank}
+        merged = sharding.gather_sensitivity(model, shard)
+        assert merged == full and list(merged.keys()) == list(full.keys())
+        # final pass: the owner installs an (oracle-made) SVDLinear, everybody else receives it
+        for n_, m_ in model.named_modules():
+            if isinstance(m_, nn.Linear):
+                m_.scaling_diag_matrix = pipe["sdm_abs_mean"][n_].clone()
+        chosen = {k: 0.6 for k in list(full.keys())[:5]}
+        for father, name, fullname, lin in enumerate_linears(model):
+            if fullname in chosen and owners[fullname] == rank:
+                ex = O.factorise_exact(lin.weight.data, 0.6, sdm=lin.scaling_diag_matrix, alpha=0.5, act_aware=True)
+                bias = lin.bias.data if lin.bias is not None else None
+                setattr(father, name, SVDLinear._from_factors(ex["A"], ex["B"], bias))
+        sharding.broadcast_factors(model, owners, list(chosen.keys()))
+        sd = model.state_dict()
+        digest = {k: float(v.double().sum()) for k, v in sd.items() if "ALinear" in k or "BLinear" in k}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, digest)
+        assert gathered[0] == gathered[1] and len(digest) >= 10          # identical factors on every rank
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_exchange_steps_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in results:
+        assert msg == "ok", f"rank {rank}:\n{msg}"
