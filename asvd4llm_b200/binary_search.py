@@ -86,6 +86,15 @@ def decompose_layers(model, chosen, default_ratio, args, layer_filter=None, batc
     Returns the number of layers replaced."""
     by_name = dict(model.named_modules())
     where = {lin: (father, name) for father, name, _, lin in enumerate_linears(model)}
+    # a weight tied to another module (OPT: lm_head <-> embed_tokens) must stay where it is: upstream's
+    # unconditional `raw_linear.to("cpu")` (:127) would drag the embedding to the CPU with it on a GPU run
+    uses = defaultdict(int)
+    for prm in model.parameters(recurse=True):
+        uses[id(prm)] += 0
+    for mod in model.modules():
+        for prm in mod._parameters.values():
+            if prm is not None:
+                uses[id(prm)] += 1
     groups = defaultdict(list)
     for layer, ratio in chosen.items():
         if ratio == default_ratio or (layer_filter is not None and not layer_filter(layer)):
@@ -102,7 +111,8 @@ def decompose_layers(model, chosen, default_ratio, args, layer_filter=None, batc
             mods = from_linear_batch([raw for _, _, raw in part], [ratio for _, ratio, _ in part], alpha=args.alpha,
                                      act_aware=args.act_aware, sigma_fuse=args.sigma_fuse, rank_align=args.rank_align)
             for (layer, _, raw), mod in zip(part, mods):
-                raw.to("cpu")                                   # upstream frees the replaced weight (:127)
+                if uses[id(raw.weight)] <= 1:
+                    raw.to("cpu")                               # upstream frees the replaced weight (:127)
                 father, name = where[raw]
                 setattr(father, name, mod)
                 done += 1

@@ -71,7 +71,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // contiguous (K) dimension of every dot product.
 constexpr int JB = 64;        // vectors per block
 constexpr int JK = 2 * JB;    // vectors per pair = order of the Gram / rotation matrices
-constexpr int GRAM_CHUNK = 512;  // columns of X reduced by one Gram CTA
+constexpr int GRAM_CHUNK = 1024;  // columns of X reduced by one Gram CTA
 
 struct SvdPlan {
   int m, n, batch;

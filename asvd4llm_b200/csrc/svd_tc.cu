@@ -19,11 +19,12 @@
 namespace asvd {
 namespace tc {
 
-constexpr int GR_STAGES = 4;
+constexpr int GR_NH = 8;                        // landing ring (TMA -> hi tiles): 8 x 16 KB in flight per SM
+constexpr int GR_NL = 3;                         // lo ring (split warps -> MMA)
 constexpr int GR_HI_BYTES = 128 * 128;           // 128 rows x 32 floats
-constexpr int GR_STAGE_BYTES = 2 * GR_HI_BYTES;  // hi + lo
-constexpr int GR_BAR_OFFSET = GR_STAGES * GR_STAGE_BYTES;
-constexpr int GR_SMEM = GR_BAR_OFFSET + 256 + 1024;
+constexpr int GR_LO_OFFSET = GR_NH * GR_HI_BYTES;
+constexpr int GR_BAR_OFFSET = GR_LO_OFFSET + GR_NL * GR_HI_BYTES;
+constexpr int GR_SMEM = GR_BAR_OFFSET + 512 + 1024;
 constexpr int GR_THREADS = 384;
 
 __device__ __forceinline__ float rna_tf32(float x) {
@@ -32,34 +33,42 @@ __device__ __forceinline__ float rna_tf32(float x) {
   return __uint_as_float(r);
 }
 
-// in-place hi/lo split of a 16 KB tile by 128 threads (layout-agnostic: same offsets in both tiles)
+// hi/lo split of a 16 KB tile by 128 threads (layout-agnostic: same offsets in both tiles); hi is rewritten in
+// place with its tf32-rounded value.  All loads are issued before the first store.
 __device__ __forceinline__ void split_tile(float4* hi, float4* lo, int t) {
+  float4 v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = hi[t + 128 * j];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    float4 v = hi[t + 128 * j];
-    float4 h = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
+    float4 h = make_float4(rna_tf32(v[j].x), rna_tf32(v[j].y), rna_tf32(v[j].z), rna_tf32(v[j].w));
     hi[t + 128 * j] = h;
-    lo[t + 128 * j] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+    lo[t + 128 * j] = make_float4(v[j].x - h.x, v[j].y - h.y, v[j].z - h.z, v[j].w - h.w);
   }
 }
 
+// precise = 1: 3-term split (fp32-accurate Gram).  precise = 0: one TF32 pass on the raw tile (the MMA ignores the low
+// mantissa bits); used while the off-diagonal cosines are still >= 1e-2, where 1e-3 relative accuracy of G only
+// perturbs the rotation angles (R stays exactly orthogonal, so nothing is lost but a little convergence speed).
 __global__ void __launch_bounds__(GR_THREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__ pairs, int pairs_per_mat, int chunks,
                int chunk_cols, int len_pad, int nv_pad, int n_items, float* __restrict__ Gpart,
-               const int* __restrict__ done) {
+               const int* __restrict__ done, int precise) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + GR_BAR_OFFSET);
-  uint64_t* split_done = full + GR_STAGES;
-  uint64_t* empty = split_done + GR_STAGES;
-  uint64_t* tfull = empty + GR_STAGES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + GR_BAR_OFFSET);   // [NH] TMA landed
+  uint64_t* empty = full + GR_NH;                                        // [NH] MMAs reading the hi tile retired
+  uint64_t* lo_ready = empty + GR_NH;                                    // [NL] split done (hi rewritten, lo written)
+  uint64_t* lo_empty = lo_ready + GR_NL;                                 // [NL]
+  uint64_t* tfull = lo_empty + GR_NL;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tmX);
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < GR_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&split_done[i], 4); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < GR_NH; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < GR_NL; ++i) { mbar_init(&lo_ready[i], 4); mbar_init(&lo_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
     fence_barrier_init();
   }
@@ -72,26 +81,27 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__
 
   if (warp == 0) {
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
+      int hs = 0; uint32_t hph = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int b = item / per_mat, p = (item % per_mat) / chunks, c = item % chunks;
         if (done[b]) continue;
         const int2 pr = pairs[p];
         const int k0 = c * chunk_cols, k1 = min(len_pad, k0 + chunk_cols);
         for (int k = k0; k < k1; k += 32) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          unsigned char* hi = smem + stage * GR_STAGE_BYTES;
-          mbar_arrive_expect_tx(&full[stage], GR_HI_BYTES);
-          tma_load_2d(hi, &tmX, &full[stage], k, b * nv_pad + pr.x * JB);
-          tma_load_2d(hi + GR_HI_BYTES / 2, &tmX, &full[stage], k, b * nv_pad + pr.y * JB);
-          if (++stage == GR_STAGES) { stage = 0; phase ^= 1; }
+          mbar_wait(&empty[hs], hph ^ 1);
+          unsigned char* hi = smem + hs * GR_HI_BYTES;
+          mbar_arrive_expect_tx(&full[hs], GR_HI_BYTES);
+          tma_load_2d(hi, &tmX, &full[hs], k, b * nv_pad + pr.x * JB);
+          tma_load_2d(hi + GR_HI_BYTES / 2, &tmX, &full[hs], k, b * nv_pad + pr.y * JB);
+          if (++hs == GR_NH) { hs = 0; hph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(2, 128, 128);
-      int stage = 0; uint32_t phase = 0;
+      int hs = 0; uint32_t hph = 0;
+      int ls = 0; uint32_t lph = 0;
       int it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int b = item / per_mat, c = item % chunks;
@@ -105,20 +115,27 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__
         const int k0 = c * chunk_cols, k1 = min(len_pad, k0 + chunk_cols);
         uint32_t acc = 0;
         for (int k = k0; k < k1; k += 32) {
-          mbar_wait(&split_done[stage], phase);
+          if (precise) mbar_wait(&lo_ready[ls], lph);
+          else mbar_wait(&full[hs], hph);
           tc_fence_after();
-          const uint32_t hi_addr = smem_u32(smem + stage * GR_STAGE_BYTES);
-          const uint64_t dh = make_desc_kmajor_sw128(hi_addr), dl = make_desc_kmajor_sw128(hi_addr + GR_HI_BYTES);
+          const uint64_t dh = make_desc_kmajor_sw128(smem_u32(smem + hs * GR_HI_BYTES));
+          const uint64_t dl = make_desc_kmajor_sw128(smem_u32(smem + GR_LO_OFFSET + ls * GR_HI_BYTES));
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {              // K = 8 tf32 = 32 bytes per step
             const uint64_t o = (uint64_t)(kk * 2);
             mma_tf32_ss(d_tmem, dh + o, dh + o, idesc, acc);
             acc = 1;
-            mma_tf32_ss(d_tmem, dl + o, dh + o, idesc, 1u);
-            mma_tf32_ss(d_tmem, dh + o, dl + o, idesc, 1u);
+            if (precise) {
+              mma_tf32_ss(d_tmem, dl + o, dh + o, idesc, 1u);
+              mma_tf32_ss(d_tmem, dh + o, dl + o, idesc, 1u);
+            }
           }
-          tc_commit(&empty[stage]);
-          if (++stage == GR_STAGES) { stage = 0; phase ^= 1; }
+          tc_commit(&empty[hs]);
+          if (++hs == GR_NH) { hs = 0; hph ^= 1; }
+          if (precise) {
+            tc_commit(&lo_empty[ls]);
+            if (++ls == GR_NL) { ls = 0; lph ^= 1; }
+          }
         }
         tc_commit(&tfull[buf]);
       }
@@ -150,21 +167,24 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && precise) {
     const int t = threadIdx.x - 256;
-    int stage = 0; uint32_t phase = 0;
+    int hs = 0; uint32_t hph = 0;
+    int ls = 0; uint32_t lph = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int b = item / per_mat, c = item % chunks;
       if (done[b]) continue;
       const int k0 = c * chunk_cols, k1 = min(len_pad, k0 + chunk_cols);
       for (int k = k0; k < k1; k += 32) {
-        mbar_wait(&full[stage], phase);
-        float4* hi = reinterpret_cast<float4*>(smem + stage * GR_STAGE_BYTES);
-        split_tile(hi, hi + GR_HI_BYTES / 16, t);
+        mbar_wait(&full[hs], hph);
+        mbar_wait(&lo_empty[ls], lph ^ 1);
+        split_tile(reinterpret_cast<float4*>(smem + hs * GR_HI_BYTES),
+                   reinterpret_cast<float4*>(smem + GR_LO_OFFSET + ls * GR_HI_BYTES), t);
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&split_done[stage]);
-        if (++stage == GR_STAGES) { stage = 0; phase ^= 1; }
+        if (lane == 0) mbar_arrive(&lo_ready[ls]);
+        if (++hs == GR_NH) { hs = 0; hph ^= 1; }
+        if (++ls == GR_NL) { ls = 0; lph ^= 1; }
       }
     }
   }
@@ -179,11 +199,12 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__
 // A = R^T (hi and lo halves) is written ONCE per CTA into tensor memory (tcgen05.st) and read from there by every
 // MMA; B = the X tile exactly as it lies in HBM (rows i, columns c contiguous: an MN-major operand), landed by TMA
 // with the 128B/32B-atom swizzle and split into hi/lo in place.  D goes back over the same rows of X.
-constexpr int UP_STAGES = 3;
+constexpr int UP_NH = 5;                           // landing ring: 5 x 32 KB in flight per SM
+constexpr int UP_NL = 2;                           // lo ring
 constexpr int UP_TN = 64;                          // columns per tile
-constexpr int UP_HI_BYTES = 128 * UP_TN * 4;       // 32 KB: two boxes of 128 rows x 32 floats
-constexpr int UP_STAGE_BYTES = 2 * UP_HI_BYTES;
-constexpr int UP_BAR_OFFSET = UP_STAGES * UP_STAGE_BYTES;
+constexpr int UP_HI_BYTES = 128 * UP_TN * 4;       // 32 KB: two groups of 128 rows x 32 floats
+constexpr int UP_LO_OFFSET = UP_NH * UP_HI_BYTES;
+constexpr int UP_BAR_OFFSET = UP_LO_OFFSET + UP_NL * UP_HI_BYTES;
 constexpr int UP_SMEM = UP_BAR_OFFSET + 256 + 1024;
 constexpr int UP_THREADS = 384;
 constexpr uint32_t UP_TMEM_A_HI = 256, UP_TMEM_A_LO = 384;   // column offsets; D buffers at 0 and 64
@@ -191,13 +212,14 @@ constexpr uint32_t UP_TMEM_A_HI = 256, UP_TMEM_A_LO = 384;   // column offsets; 
 __global__ void __launch_bounds__(UP_THREADS, 1)
 update_tc_kernel(const __grid_constant__ CUtensorMap tmX, float* __restrict__ X, int64_t mat_stride, int ldx,
                  const int2* __restrict__ pairs, int pairs_per_mat, int nv_pad, int tiles_total, int tiles_per_cta,
-                 const float* __restrict__ Rt, const int* __restrict__ pairflag, const int* __restrict__ done) {
+                 const float* __restrict__ R, const int* __restrict__ pairflag, const int* __restrict__ done) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + UP_BAR_OFFSET);
-  uint64_t* split_done = full + UP_STAGES;
-  uint64_t* empty = split_done + UP_STAGES;
-  uint64_t* tfull = empty + UP_STAGES;
+  uint64_t* empty = full + UP_NH;
+  uint64_t* lo_ready = empty + UP_NH;
+  uint64_t* lo_empty = lo_ready + UP_NL;
+  uint64_t* tfull = lo_empty + UP_NL;
   uint64_t* tempty = tfull + 2;
   uint64_t* a_ready = tempty + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_ready + 1);
@@ -213,7 +235,8 @@ update_tc_kernel(const __grid_constant__ CUtensorMap tmX, float* __restrict__ X,
 
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tmX);
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < UP_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&split_done[i], 4); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < UP_NH; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < UP_NL; ++i) { mbar_init(&lo_ready[i], 4); mbar_init(&lo_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
     mbar_init(a_ready, 4);
     fence_barrier_init();
@@ -230,14 +253,14 @@ update_tc_kernel(const __grid_constant__ CUtensorMap tmX, float* __restrict__ X,
       for (int t = 0; t < ntiles; ++t) {
         const int c0 = (tile0 + t) * UP_TN;
         mbar_wait(&empty[stage], phase ^ 1);
-        unsigned char* hi = smem + stage * UP_STAGE_BYTES;
+        unsigned char* hi = smem + stage * UP_HI_BYTES;
         mbar_arrive_expect_tx(&full[stage], UP_HI_BYTES);
         // box = 64 rows x 32 floats; rows 0-63 of the tile are block I, rows 64-127 block J; two 32-column groups
         for (int g = 0; g < 2; ++g) {
           tma_load_2d(hi + g * 16384, &tmX, &full[stage], c0 + g * 32, b * nv_pad + pr.x * JB);
           tma_load_2d(hi + g * 16384 + 8192, &tmX, &full[stage], c0 + g * 32, b * nv_pad + pr.y * JB);
         }
-        if (++stage == UP_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == UP_NH) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -246,45 +269,46 @@ update_tc_kernel(const __grid_constant__ CUtensorMap tmX, float* __restrict__ X,
       mbar_wait(a_ready, 0);
       tc_fence_after();
       int stage = 0; uint32_t phase = 0;
+      int ls = 0; uint32_t lph = 0;
       for (int t = 0; t < ntiles; ++t) {
         const int buf = t & 1;
         const uint32_t use = (uint32_t)(t >> 1);
         mbar_wait(&tempty[buf], (use & 1) ^ 1);
-        mbar_wait(&split_done[stage], phase);
+        mbar_wait(&lo_ready[ls], lph);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * UP_TN);
-        const uint32_t hi_addr = smem_u32(smem + stage * UP_STAGE_BYTES);
+        const uint32_t hi_addr = smem_u32(smem + stage * UP_HI_BYTES);
+        const uint32_t lo_addr = smem_u32(smem + UP_LO_OFFSET + ls * UP_HI_BYTES);
 #pragma unroll
         for (int k = 0; k < 16; ++k) {                    // K = 8 rows of the tile per step = 1024 bytes
           const uint64_t bh = make_desc_mnmajor_sw128_32b(hi_addr + k * 1024, 16384);
-          const uint64_t bl = make_desc_mnmajor_sw128_32b(hi_addr + UP_HI_BYTES + k * 1024, 16384);
+          const uint64_t bl = make_desc_mnmajor_sw128_32b(lo_addr + k * 1024, 16384);
           mma_tf32_ts(d_tmem, tmem_base + UP_TMEM_A_HI + k * 8, bh, idesc, k ? 1u : 0u);
           mma_tf32_ts(d_tmem, tmem_base + UP_TMEM_A_LO + k * 8, bh, idesc, 1u);
           mma_tf32_ts(d_tmem, tmem_base + UP_TMEM_A_HI + k * 8, bl, idesc, 1u);
         }
-        tc_commit(&empty[stage]);
-        tc_commit(&tfull[buf]);
-        if (++stage == UP_STAGES) { stage = 0; phase ^= 1; }
+        tc_commit(&lo_empty[ls]);
+        tc_commit(&tfull[buf]);          // the hi slot is handed to the epilogue, which overwrites it with D
+        if (++stage == UP_NH) { stage = 0; phase ^= 1; }
+        if (++ls == UP_NL) { ls = 0; lph ^= 1; }
       }
     }
   } else if (warp >= 4 && warp < 8) {
     const int q = warp - 4;
     const int j = q * 32 + lane;                           // output vector of this thread = TMEM lane
-    {   // A = R^T: row j of Rt -> hi/lo -> tensor memory columns [256,384) and [384,512)
-      const float4* src = reinterpret_cast<const float4*>(Rt + (int64_t)idx * (JK * JK) + j * JK);
+    {   // A = R^T: thread j gathers column j of R (coalesced across the warp) -> hi/lo -> tensor memory
+      const float* src = R + (int64_t)idx * (JK * JK) + j;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
+        float x[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) x[e] = src[(c * 32 + e) * JK];
         uint32_t h[32], l[32];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float4 v = src[c * 8 + e];
-          float x[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float hh = rna_tf32(x[i]);
-            h[e * 4 + i] = __float_as_uint(hh);
-            l[e * 4 + i] = __float_as_uint(x[i] - hh);
-          }
+        for (int e = 0; e < 32; ++e) {
+          const float hh = rna_tf32(x[e]);
+          h[e] = __float_as_uint(hh);
+          l[e] = __float_as_uint(x[e] - hh);
         }
         tmem_st_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + UP_TMEM_A_HI + c * 32, h);
         tmem_st_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + UP_TMEM_A_LO + c * 32, l);
@@ -294,41 +318,73 @@ update_tc_kernel(const __grid_constant__ CUtensorMap tmX, float* __restrict__ X,
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready);
     }
-    const int vec = (j < JB) ? pr.x * JB + j : pr.y * JB + (j - JB);
-    float* xrow = X + b * mat_stride + (int64_t)vec * ldx;
+    // D tile -> the tile's own landing slot, in the layout the TMA wrote it (rows of 128 B, 32-byte chunks XOR row&3)
+    // -> TMA store over the same rows of X.  The slot returns to the producer once the store has read it.
+    const int row_off = j * 128;
+    const int sw = j & 3;
+    int stage = 0;
+    int pending_stage = -1;
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
       const uint32_t use = (uint32_t)(t >> 1);
       mbar_wait(&tfull[buf], use & 1);
       tc_fence_after();
-      const int c0 = (tile0 + t) * UP_TN;
+      unsigned char* slot = smem + stage * UP_HI_BYTES;
 #pragma unroll
-      for (int c = 0; c < UP_TN / 32; ++c) {
+      for (int g = 0; g < UP_TN / 32; ++g) {
         uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * UP_TN + c * 32), v);
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * UP_TN + g * 32), v);
         tmem_ld_wait();
-        float4* dst = reinterpret_cast<float4*>(xrow + c0 + c * 32);
+        unsigned char* rowp = slot + g * 16384 + row_off;
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-          dst[e] = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]),
-                               __uint_as_float(v[4 * e + 3]));
+        for (int ch = 0; ch < 4; ++ch) {            // 32-byte chunk ch of the 128-byte row lands at chunk (ch ^ (row & 3))
+          float4* dst = reinterpret_cast<float4*>(rowp + ((ch ^ sw) << 5));
+          dst[0] = make_float4(__uint_as_float(v[8 * ch]), __uint_as_float(v[8 * ch + 1]), __uint_as_float(v[8 * ch + 2]),
+                               __uint_as_float(v[8 * ch + 3]));
+          dst[1] = make_float4(__uint_as_float(v[8 * ch + 4]), __uint_as_float(v[8 * ch + 5]), __uint_as_float(v[8 * ch + 6]),
+                               __uint_as_float(v[8 * ch + 7]));
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps
+      if (warp == 4 && lane == 0) {
+        const int c0 = (tile0 + t) * UP_TN;
+        for (int g = 0; g < 2; ++g) {
+          tma_store_2d(&tmX, slot + g * 16384, c0 + g * 32, b * nv_pad + pr.x * JB);
+          tma_store_2d(&tmX, slot + g * 16384 + 8192, c0 + g * 32, b * nv_pad + pr.y * JB);
+        }
+        tma_store_commit();
+        if (pending_stage >= 0) {                              // previous tile's store has finished reading its slot
+          tma_store_wait_read<1>();
+          mbar_arrive(&empty[pending_stage]);
+        }
+        pending_stage = stage;
+      }
+      if (++stage == UP_NH) stage = 0;
+    }
+    if (warp == 4 && lane == 0) {
+      tma_store_wait<0>();                                     // all stores complete (globally visible) before exit
+      if (pending_stage >= 0) mbar_arrive(&empty[pending_stage]);
     }
   } else if (warp >= 8) {
     const int t128 = threadIdx.x - 256;
     int stage = 0; uint32_t phase = 0;
+    int ls = 0; uint32_t lph = 0;
     for (int t = 0; t < ntiles; ++t) {
       mbar_wait(&full[stage], phase);
-      float4* hi = reinterpret_cast<float4*>(smem + stage * UP_STAGE_BYTES);
-      split_tile(hi, hi + UP_HI_BYTES / 16, t128);
-      split_tile(hi + 1024, hi + UP_HI_BYTES / 16 + 1024, t128);
+      mbar_wait(&lo_empty[ls], lph ^ 1);
+      float4* hi = reinterpret_cast<float4*>(smem + stage * UP_HI_BYTES);
+      float4* lo = reinterpret_cast<float4*>(smem + UP_LO_OFFSET + ls * UP_HI_BYTES);
+      split_tile(hi, lo, t128);
+      split_tile(hi + 1024, lo + 1024, t128);
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&split_done[stage]);
-      if (++stage == UP_STAGES) { stage = 0; phase ^= 1; }
+      if (lane == 0) mbar_arrive(&lo_ready[ls]);
+      if (++stage == UP_NH) { stage = 0; phase ^= 1; }
+      if (++ls == UP_NL) { ls = 0; lph ^= 1; }
     }
   }
   tc_fence_before();
@@ -354,7 +410,7 @@ bool make_x_tmap(CUtensorMap* map, const float* X, int batch, int nv_pad, int le
 }
 
 cudaError_t launch_gram_tc(const CUtensorMap& tmX, const int2* pairs, int pairs_per_mat, int chunks, int chunk_cols,
-                           int len_pad, int nv_pad, int batch, float* Gpart, const int* done, cudaStream_t st) {
+                           int len_pad, int nv_pad, int batch, float* Gpart, const int* done, int precise, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM);
@@ -364,7 +420,7 @@ cudaError_t launch_gram_tc(const CUtensorMap& tmX, const int2* pairs, int pairs_
   const int n_items = batch * pairs_per_mat * chunks;
   const int grid = n_items < sm_count() ? n_items : sm_count();
   gram_tc_kernel<<<grid, GR_THREADS, GR_SMEM, st>>>(tmX, pairs, pairs_per_mat, chunks, chunk_cols, len_pad, nv_pad, n_items,
-                                                    Gpart, done);
+                                                    Gpart, done, precise);
   return cudaGetLastError();
 }
 
@@ -376,7 +432,7 @@ bool make_x_tmap_mn(CUtensorMap* map, const float* X, int batch, int nv_pad, int
 }
 
 cudaError_t launch_update_tc(const CUtensorMap& tmX, float* X, int64_t mat_stride, int ldx, const int2* pairs,
-                             int pairs_per_mat, int nv_pad, int len_pad, int batch, const float* Rt, const int* pairflag,
+                             int pairs_per_mat, int nv_pad, int len_pad, int batch, const float* R, const int* pairflag,
                              const int* done, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
@@ -391,7 +447,7 @@ cudaError_t launch_update_tc(const CUtensorMap& tmX, float* X, int64_t mat_strid
   if (tiles_per_cta < 8) tiles_per_cta = tiles_total < 8 ? tiles_total : 8;
   ctas_x = (tiles_total + tiles_per_cta - 1) / tiles_per_cta;
   update_tc_kernel<<<dim3(ctas_x, pairs_per_mat, batch), UP_THREADS, UP_SMEM, st>>>(tmX, X, mat_stride, ldx, pairs, pairs_per_mat,
-                                                                                  nv_pad, tiles_total, tiles_per_cta, Rt,
+                                                                                  nv_pad, tiles_total, tiles_per_cta, R,
                                                                                   pairflag, done);
   return cudaGetLastError();
 }
