@@ -2,12 +2,13 @@
 // K-major, as activations [tokens, features] and nn.Linear weights [out, in] are), fp32 accumulation in TMEM.
 //
 // Persistent, warp-specialised, one CTA per SM:
-//   warp 0     TMA producer : 128 x 64 tile of A and BN x 64 tile of B per stage (128-byte swizzle), 4 stages
+//   warp 0     TMA producer : 128 x 64 tile of A and BN x 64 tile of B per stage (128-byte swizzle), 3 stages
 //   warp 1     MMA issuer   : one elected thread issues 4 x tcgen05.mma (M=128, N=BN, K=16) per stage into one of
 //                             two TMEM accumulators; tcgen05.commit releases the stage / publishes the accumulator
 //   warp 2     TMEM allocator (2 x BN columns)
-//   warps 4-7  epilogue     : tcgen05.ld (32 lanes x 32 columns per warp and step) -> + bias -> 16-bit -> global,
-//                             overlapped with the next tile's MMAs through the second accumulator
+//   warps 4-11 epilogue     : tcgen05.ld (32 lanes x 32 columns per warp and step) -> + bias -> 16-bit -> swizzled
+//                             staging tile in shared memory -> TMA store (full 128-byte lines), overlapped with the
+//                             next tile's MMAs through the second accumulator
 // SVDLinear.forward = two launches: t = x B^T, y = t A^T + b (the [tokens, r] intermediate stays L2-resident for
 // the sizes of BASELINE config 4: 64 Ki x 256 x 2 B = 32 MiB per 128 MiB L2).
 #include "common.cuh"
@@ -19,14 +20,16 @@ namespace tc {
 
 constexpr int BM = 128;
 constexpr int BK = 64;            // 16-bit elements per stage row = 128 bytes = one swizzle atom
-constexpr int STAGES = 4;
-constexpr int GEMM_THREADS = 256;
+constexpr int STAGES = 3;
+constexpr int GEMM_THREADS = 384;      // warps 0-3: producer / MMA / TMEM alloc / spare; warps 4-11: epilogue
+constexpr int STAGING_HALF = BM * 128 * 2;   // one 128-column half of the output tile: 2 groups of [128 rows x 128 B]
 
 template <int BN> struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = STAGING_OFFSET + (BN / 128) * STAGING_HALF;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + tmem pointer + alignment slack
 };
 
@@ -42,8 +45,8 @@ template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, fl
 
 template <typename T, int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, T* __restrict__ C,
-               int64_t ldc, const T* __restrict__ bias, int M, int N, int K) {
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const T* __restrict__ bias, int M, int N, int K) {
   using S = GemmSmem<BN>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -61,10 +64,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * (BN / 128)); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr, 2 * BN);
@@ -115,25 +119,29 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    const int q = warp - 4;                              // TMEM lane quadrant of this warp
+    // epilogue: warp = (TMEM lane quadrant q, 128-column half h).  Accumulator -> registers -> + bias -> 16-bit ->
+    // staging tile in shared memory (rows of 128 B, 16-byte chunks XOR row&7 = the 128-byte TMA swizzle) -> TMA store.
+    const int q = (warp - 4) & 3, h = (warp - 4) >> 2;
+    const bool active = h < BN / 128;
+    const int r = q * 32 + lane;                                  // row of the tile = TMEM lane
+    unsigned char* stg = smem + S::STAGING_OFFSET + h * STAGING_HALF;
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       const int m0 = (t / num_n) * BM, n0 = (t % num_n) * BN;
+      if (!active) continue;
       mbar_wait(&tfull[buf], use & 1);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < M;
-      T* crow = C + (int64_t)row * ldc;
-      const bool vec_ok = ((ldc * (int64_t)sizeof(T)) % 16 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+      // the previous tile's store must have finished reading this half's staging buffer
+      if (q == 0 && lane == 0) tma_store_wait_read<0>();
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + h) : "memory");
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32), v);
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + h * 128 + c * 32), v);
         tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        if (row_ok && col0 < N) {
+        const int col0 = n0 + h * 128 + c * 32;
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -141,21 +149,28 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (col0 + j < N) f[j] += to_f32<T>(bias[col0 + j]);
         }
-        if (vec_ok && col0 + 32 <= N) {
-          uint4* dst = reinterpret_cast<uint4*>(crow + col0);
+        // 32 columns = 64 bytes = chunks 4*(c&1) .. +3 of the 128-byte row of group c>>1
+        unsigned char* rowp = stg + (c >> 1) * (BM * 128) + r * 128;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            dst[j] = make_uint4(pack2<T>(f[8 * j], f[8 * j + 1]), pack2<T>(f[8 * j + 2], f[8 * j + 3]),
-                                pack2<T>(f[8 * j + 4], f[8 * j + 5]), pack2<T>(f[8 * j + 6], f[8 * j + 7]));
-        } else {
-          for (int j = 0; j < 32 && col0 + j < N; ++j) crow[col0 + j] = from_f32<T>(f[j]);
-        }
+        for (int j = 0; j < 4; ++j) {
+          const int chunk = ((c & 1) * 4 + j) ^ (r & 7);
+          *reinterpret_cast<uint4*>(rowp + chunk * 16) =
+              make_uint4(pack2<T>(f[8 * j], f[8 * j + 1]), pack2<T>(f[8 * j + 2], f[8 * j + 3]),
+                         pack2<T>(f[8 * j + 4], f[8 * j + 5]), pack2<T>(f[8 * j + 6], f[8 * j + 7]));
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
+      fence_proxy_async_smem();
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + h) : "memory");
+      if (q == 0 && lane == 0) {
+        tma_store_2d(&tmC, stg, n0 + h * 128, m0);
+        tma_store_2d(&tmC, stg + BM * 128, n0 + h * 128 + 64, m0);
+        tma_store_commit();
+      }
     }
+    if (active && q == 0 && lane == 0) tma_store_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -163,7 +178,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 template <typename T, int BN>
-static cudaError_t launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, T* C, int64_t ldc, const T* bias, int M, int N,
+static cudaError_t launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const T* bias, int M, int N,
                              int K, int sms, cudaStream_t st) {
   using S = GemmSmem<BN>;
   static bool attr = false;
@@ -173,7 +188,7 @@ static cudaError_t launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, T* 
     attr = true;
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  gemm_tn_kernel<T, BN><<<tiles < sms ? tiles : sms, GEMM_THREADS, S::TOTAL, st>>>(tmA, tmB, C, ldc, bias, M, N, K);
+  gemm_tn_kernel<T, BN><<<tiles < sms ? tiles : sms, GEMM_THREADS, S::TOTAL, st>>>(tmA, tmB, tmC, bias, M, N, K);
   return cudaGetLastError();
 }
 
@@ -182,7 +197,7 @@ template <typename T>
 int gemm_tn_tc(const T* A, int64_t lda, const T* B, int64_t ldb, T* C, int64_t ldc, const T* bias, int M, int N, int K,
                cudaStream_t st) {
   auto ok = [](const void* p, int64_t ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld * 2) % 16 == 0; };
-  if (!ok(A, lda) || !ok(B, ldb) || K < 8) return 1;
+  if (!ok(A, lda) || !ok(B, ldb) || !ok(C, ldc) || K < 8) return 1;
   static int sms = 0;
   if (!sms) {
     int dev = 0;
@@ -190,12 +205,13 @@ int gemm_tn_tc(const T* A, int64_t lda, const T* B, int64_t ldb, T* C, int64_t l
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const CUtensorMapDataType dt = std::is_same<T, __half>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC;
   const int BN = (N > 128) ? 256 : 128;
   if (!make_tmap_2d(&tmA, dt, 2, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK)) return -1;
   if (!make_tmap_2d(&tmB, dt, 2, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)BN, BK)) return -1;
-  cudaError_t e = (BN == 256) ? launch_tn<T, 256>(tmA, tmB, C, ldc, bias, M, N, K, sms, st)
-                              : launch_tn<T, 128>(tmA, tmB, C, ldc, bias, M, N, K, sms, st);
+  if (!make_tmap_2d(&tmC, dt, 2, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, BM, 64)) return -1;
+  cudaError_t e = (BN == 256) ? launch_tn<T, 256>(tmA, tmB, tmC, bias, M, N, K, sms, st)
+                              : launch_tn<T, 128>(tmA, tmB, tmC, bias, M, N, K, sms, st);
   return e == cudaSuccess ? 0 : -2;
 }
 

@@ -240,18 +240,16 @@ constexpr size_t SOLVE_SMEM = sizeof(float) * (2 * JK * SLD) + sizeof(float2) * 
 // Returns (alpha, -beta) and updates the two scales.
 __device__ __forceinline__ float2 jacobi_scaled(float ghat_pp, float ghat_qq, float ghat_pq, float& dp, float& dq) {
   const float app = dp * dp * ghat_pp, aqq = dq * dq * ghat_qq, apq = dp * dq * ghat_pq;
+  const float ratio = __fdividef(dp, dq);                       // independent of the chain below
   float c = 1.f, t = 0.f;
-  if (fabsf(apq) > 1e-8f * sqrtf(fmaxf(app, 0.f) * fmaxf(aqq, 0.f)) && apq != 0.f) {
+  if (apq * apq > 1e-16f * (app * aqq) && apq != 0.f) {         // |cos| > 1e-8
     const float tau = __fdividef(aqq - app, 2.f * apq);
-    t = __fdividef(copysignf(1.f, tau), fabsf(tau) + sqrtf(fmaf(tau, tau, 1.f)));
+    const float w = fmaf(tau, tau, 1.f);
+    t = __fdividef(copysignf(1.f, tau), fabsf(tau) + w * rsqrtf(w));   // sqrt(w) = w * rsqrt(w); any t gives an exact rotation
     c = rsqrtf(fmaf(t, t, 1.f));
   }
-  float alpha = 0.f, nbeta = 0.f;
-  if (t != 0.f) {
-    const float ratio = __fdividef(dp, dq);
-    alpha = t * ratio;
-    nbeta = -__fdividef(t, ratio);
-  }
+  const float alpha = t * ratio;
+  const float nbeta = (t != 0.f) ? -__fdividef(t, ratio) : 0.f;
   const float ndp = c * dq, ndq = c * dp;
   dp = ndp; dq = ndq;
   return make_float2(alpha, nbeta);
@@ -268,7 +266,7 @@ __device__ __forceinline__ float2 jacobi_scaled(float ghat_pp, float ghat_qq, fl
 __global__ void __launch_bounds__(SOLVE_THREADS, 1)
 solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, float* __restrict__ Rout,
              int* __restrict__ pairflag, unsigned* __restrict__ maxoff_bits, int* __restrict__ status,
-             const int* __restrict__ done, float tol, int transpose_out) {
+             const int* __restrict__ done, float tol, int transpose_out, int dbg_steps) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* G = reinterpret_cast<float*>(smem_raw);            // [JK][SLD]; later E = R^T R
   float* Rs = G + JK * SLD;                                 // [JK][SLD]; R in sorted column order (after the sweep)
@@ -298,14 +296,6 @@ solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, flo
     G[(e >> 7) * SLD + (e & (JK - 1))] = s;
   }
   if (tid < JK) dsc[tid] = 1.f;
-  if (tid < JK / 2) {            // block tables: row s of the triangle starts at s*n - s(s-1)/2
-    int off = tid * (JK / 2) - tid * (tid - 1) / 2;
-    for (int t = tid; t < JK / 2; ++t) tab_even[off + (t - tid)] = make_uchar2(tid, t);
-    if (tid < JK / 2 - 1) {
-      off = tid * (JK / 2 - 1) - tid * (tid - 1) / 2;
-      for (int t = tid; t < JK / 2 - 1; ++t) tab_odd[off + (t - tid)] = make_uchar2(tid, t);
-    }
-  }
   __syncthreads();
   // convergence measure of this pair at visit time: max |cos| between any two of its 128 vectors
   float mx = 0.f;
@@ -347,32 +337,187 @@ solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, flo
   }
   if (tid == 0) pairflag[idx] = 1;
 
-  // ---- one odd-even sweep.  The two roles run separate loops (so each gets its own register allocation) and
-  // meet at named barrier 1 twice per step: after the rotation parameters are published and after they are applied.
+  // ---- one odd-even sweep, everything in registers.
+  // G threads (256): thread (a, c) keeps the 8x8 patch G[8a.., 8c..] of the FULL symmetric matrix in registers.
+  //   Even steps pair rows/columns (2t, 2t+1): entirely inside the patches, no data movement.  Odd steps pair
+  //   (2t+1, 2t+2): three pairs inside a patch, one straddling two patches; the straddling rows (then columns) are
+  //   exchanged through a small shared buffer.
+  // R threads (256): thread (row, half) keeps 64 columns of one row of R in registers (column rotations only).
+  // Rotation parameters come from the diagonal and first super-diagonal, which the patch owners publish each step.
   auto bar_all = [] { asm volatile("bar.sync 1, %0;" ::"n"(SOLVE_THREADS) : "memory"); };
   auto bar_g = [] { asm volatile("bar.sync 2, %0;" ::"n"(SOLVE_GTHREADS) : "memory"); };
-  if (tid < SOLVE_RTHREADS) {
+  float* gd = diag;                  // [JK]   current diagonal (scaled form)
+  float* xbuf = Rs;                  // exchange area inside the (not yet used) Rs region
+  float* rowF = xbuf;                // [16][JK] first row of every patch row
+  float* rowL = rowF + 16 * JK;      // [16][JK] last row
+  float* colF = rowL + 16 * JK;      // [16][JK] first column of every patch column
+  float* colL = colF + 16 * JK;      // [16][JK] last column
+  float* go = colL + 16 * JK;        // [JK]   first super-diagonal G(i, i+1)
+  if (tid < SOLVE_GTHREADS) {
+    const int pa = tid >> 4, pc = tid & 15;
+    float g[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 x0 = *reinterpret_cast<const float4*>(&G[(8 * pa + i) * SLD + 8 * pc]);
+      const float4 x1 = *reinterpret_cast<const float4*>(&G[(8 * pa + i) * SLD + 8 * pc + 4]);
+      g[i][0] = x0.x; g[i][1] = x0.y; g[i][2] = x0.z; g[i][3] = x0.w;
+      g[i][4] = x1.x; g[i][5] = x1.y; g[i][6] = x1.z; g[i][7] = x1.w;
+    }
+    const int dbg_mode = dbg_steps >> 8;
+    for (int st = 0; st < 2 * (dbg_steps & 0xff); ++st) {
+      const int odd = st & 1;
+      // publish the entries the rotation parameters are computed from
+      if (dbg_mode & 8) {
+      } else if (pa == pc) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gd[8 * pa + i] = g[i][i];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) go[8 * pa + i] = g[i][i + 1];
+      } else if (pc == pa + 1) {
+        go[8 * pa + 7] = g[7][0];
+      }
+      bar_all();           // gd / go visible
+      bar_all();           // cs / dsc written by the parameter threads
+      if (dbg_mode & 2) continue;
+      if (!odd) {
+#pragma unroll
+        for (int lp = 0; lp < 4; ++lp) {                 // rows (2lp, 2lp+1): new = (g1 + alpha g0, g0 - beta g1)
+          const float2 q = cs[4 * pa + lp];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ASVD_ROT_SWAP(g[2 * lp][j], g[2 * lp + 1][j], q);
+        }
+#pragma unroll
+        for (int lp = 0; lp < 4; ++lp) {                 // columns, same rule
+          const float2 q = cs[4 * pc + lp];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ASVD_ROT_SWAP(g[i][2 * lp], g[i][2 * lp + 1], q);
+        }
+      } else {
+        // rows: exchange the boundary rows with the patches above / below
+        *reinterpret_cast<float4*>(&rowF[pa * JK + 8 * pc]) = make_float4(g[0][0], g[0][1], g[0][2], g[0][3]);
+        *reinterpret_cast<float4*>(&rowF[pa * JK + 8 * pc + 4]) = make_float4(g[0][4], g[0][5], g[0][6], g[0][7]);
+        *reinterpret_cast<float4*>(&rowL[pa * JK + 8 * pc]) = make_float4(g[7][0], g[7][1], g[7][2], g[7][3]);
+        *reinterpret_cast<float4*>(&rowL[pa * JK + 8 * pc + 4]) = make_float4(g[7][4], g[7][5], g[7][6], g[7][7]);
+        bar_g();
+        {
+          float below[8], above[8];
+          if (pa < 15) {
+            const float4 x0 = *reinterpret_cast<const float4*>(&rowF[(pa + 1) * JK + 8 * pc]);
+            const float4 x1 = *reinterpret_cast<const float4*>(&rowF[(pa + 1) * JK + 8 * pc + 4]);
+            below[0] = x0.x; below[1] = x0.y; below[2] = x0.z; below[3] = x0.w;
+            below[4] = x1.x; below[5] = x1.y; below[6] = x1.z; below[7] = x1.w;
+          }
+          if (pa > 0) {
+            const float4 x0 = *reinterpret_cast<const float4*>(&rowL[(pa - 1) * JK + 8 * pc]);
+            const float4 x1 = *reinterpret_cast<const float4*>(&rowL[(pa - 1) * JK + 8 * pc + 4]);
+            above[0] = x0.x; above[1] = x0.y; above[2] = x0.z; above[3] = x0.w;
+            above[4] = x1.x; above[5] = x1.y; above[6] = x1.z; above[7] = x1.w;
+          }
+#pragma unroll
+          for (int lp = 0; lp < 3; ++lp) {               // rows (2lp+1, 2lp+2), pair index 4pa + lp
+            const float2 q = cs[4 * pa + lp];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ASVD_ROT_SWAP(g[2 * lp + 1][j], g[2 * lp + 2][j], q);
+          }
+          if (pa < 15) {                                 // row 8pa+7 is the p side of pair 4pa+3: new = below + alpha own
+            const float2 q = cs[4 * pa + 3];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[7][j] = fmaf(q.x, g[7][j], below[j]);
+          }
+          if (pa > 0) {                                  // row 8pa is the q side of pair 4pa-1: new = above - beta own
+            const float2 q = cs[4 * pa - 1];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[0][j] = fmaf(q.y, g[0][j], above[j]);
+          }
+        }
+        // columns: exchange the (row-rotated) boundary columns with the patches left / right
+        *reinterpret_cast<float4*>(&colF[pc * JK + 8 * pa]) = make_float4(g[0][0], g[1][0], g[2][0], g[3][0]);
+        *reinterpret_cast<float4*>(&colF[pc * JK + 8 * pa + 4]) = make_float4(g[4][0], g[5][0], g[6][0], g[7][0]);
+        *reinterpret_cast<float4*>(&colL[pc * JK + 8 * pa]) = make_float4(g[0][7], g[1][7], g[2][7], g[3][7]);
+        *reinterpret_cast<float4*>(&colL[pc * JK + 8 * pa + 4]) = make_float4(g[4][7], g[5][7], g[6][7], g[7][7]);
+        bar_g();
+        {
+          float right[8], left[8];
+          if (pc < 15) {
+            const float4 x0 = *reinterpret_cast<const float4*>(&colF[(pc + 1) * JK + 8 * pa]);
+            const float4 x1 = *reinterpret_cast<const float4*>(&colF[(pc + 1) * JK + 8 * pa + 4]);
+            right[0] = x0.x; right[1] = x0.y; right[2] = x0.z; right[3] = x0.w;
+            right[4] = x1.x; right[5] = x1.y; right[6] = x1.z; right[7] = x1.w;
+          }
+          if (pc > 0) {
+            const float4 x0 = *reinterpret_cast<const float4*>(&colL[(pc - 1) * JK + 8 * pa]);
+            const float4 x1 = *reinterpret_cast<const float4*>(&colL[(pc - 1) * JK + 8 * pa + 4]);
+            left[0] = x0.x; left[1] = x0.y; left[2] = x0.z; left[3] = x0.w;
+            left[4] = x1.x; left[5] = x1.y; left[6] = x1.z; left[7] = x1.w;
+          }
+#pragma unroll
+          for (int lp = 0; lp < 3; ++lp) {
+            const float2 q = cs[4 * pc + lp];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ASVD_ROT_SWAP(g[i][2 * lp + 1], g[i][2 * lp + 2], q);
+          }
+          if (pc < 15) {
+            const float2 q = cs[4 * pc + 3];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i][7] = fmaf(q.x, g[i][7], right[i]);
+          }
+          if (pc > 0) {
+            const float2 q = cs[4 * pc - 1];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i][0] = fmaf(q.y, g[i][0], left[i]);
+          }
+        }
+      }
+    }
+    // final diagonal (true norms) for the sort
+    bar_all();             // R threads are done reading cs; exchange area is free
+    if (pa == pc) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) gd[8 * pa + i] = dsc[8 * pa + i] * dsc[8 * pa + i] * g[i][i];
+    }
+    bar_g();
+    if (tid < JK) {
+      const float d = gd[tid];
+      int rank = 0;
+      for (int j = 0; j < JK; ++j) {
+        const float e = gd[j];
+        rank += (e > d) || (e == d && j < tid);
+      }
+      dest[tid] = rank;
+    }
+    bar_all();             // dest[] ready
+  } else {
     // thread = (row, half): 64 consecutive columns of one row of R in registers
-    const int row = tid >> 1, half = tid & 1;
+    const int rt = tid - SOLVE_GTHREADS;
+    const int row = rt >> 1, half = rt & 1;
     float r[JK / 2];
 #pragma unroll
     for (int j = 0; j < JK / 2; ++j) r[j] = (half * (JK / 2) + j == row) ? 1.f : 0.f;
     const float2* cs_h = cs + half * (JK / 4);
-    for (int st2 = 0; st2 < JK / 2; ++st2) {
-      bar_all();
-      // even step: local pairs (2j, 2j+1), parameters cs[32*half + j]; loads batched 16 at a time
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        float2 q[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) q[j] = cs_h[g * 16 + j];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) ASVD_ROT_SWAP(r[2 * (g * 16 + j)], r[2 * (g * 16 + j) + 1], q[j]);
+    const int dbg_mode = dbg_steps >> 8;
+    for (int st = 0; st < 2 * (dbg_steps & 0xff); ++st) {
+      const int odd = st & 1;
+      bar_all();           // gd / go published
+      if (!(dbg_mode & 1) && rt < JK / 2 - odd) {                           // rotation parameters of pair rt
+        const int pp = 2 * rt + odd;
+        float dp = dsc[pp], dq = dsc[pp + 1];
+        cs[rt] = jacobi_scaled(gd[pp], gd[pp + 1], go[pp], dp, dq);
+        dsc[pp] = dp; dsc[pp + 1] = dq;
       }
-      bar_all();
-      bar_all();
-      // odd step: local pairs (2j+1, 2j+2) for j < 31 with cs[32*half + j]; global pair (63,64) straddles the halves
-      {
+      bar_all();           // cs visible
+      if (dbg_mode & 4) continue;
+      if (!odd) {
+        // local pairs (2j, 2j+1), parameters cs[32*half + j]; loads batched 16 at a time
+#pragma unroll
+        for (int gq = 0; gq < 2; ++gq) {
+          float2 q[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) q[j] = cs_h[gq * 16 + j];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) ASVD_ROT_SWAP(r[2 * (gq * 16 + j)], r[2 * (gq * 16 + j) + 1], q[j]);
+        }
+      } else {
+        // local pairs (2j+1, 2j+2) for j < 31 with cs[32*half + j]; global pair (63,64) straddles the halves
         float2 q[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) q[j] = cs_h[j];
@@ -388,101 +533,11 @@ solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, flo
         if (half == 0) r[JK / 2 - 1] = fmaf(qb.x, mine, other);             // a' = b + alpha a
         else r[0] = fmaf(qb.y, mine, other);                                // b' = a - beta b
       }
-      bar_all();
     }
-    bar_all();                                   // dest[] is ready
+    bar_all();             // matches the G threads' barrier before the final diagonal
+    bar_all();             // dest[] ready
 #pragma unroll
     for (int j = 0; j < JK / 2; ++j) Rs[row * SLD + dest[half * (JK / 2) + j]] = r[j] * dsc[half * (JK / 2) + j];
-  } else {
-    const int gt = tid - SOLVE_RTHREADS;
-    // each G thread owns the same (up to) 9 upper-triangle blocks on every even step and 8-9 on every odd step:
-    // their coordinates stay in registers so a step is "load everything, then compute and store everything"
-    constexpr int MAXB = (NB_EVEN + SOLVE_GTHREADS - 1) / SOLVE_GTHREADS;   // 9
-    uchar2 blk_e[MAXB], blk_o[MAXB];
-#pragma unroll
-    for (int i = 0; i < MAXB; ++i) {
-      const int e = gt + SOLVE_GTHREADS * i;
-      blk_e[i] = e < NB_EVEN ? tab_even[e] : make_uchar2(255, 255);
-      blk_o[i] = e < NB_ODD ? tab_odd[e] : make_uchar2(255, 255);
-    }
-    for (int st2 = 0; st2 < JK / 2; ++st2) {
-#pragma unroll 1
-      for (int odd = 0; odd < 2; ++odd) {
-        if (gt < JK / 2 - odd) {
-          const int pp = 2 * gt + odd;
-          float dp = dsc[pp], dq = dsc[pp + 1];
-          cs[gt] = jacobi_scaled(G[pp * SLD + pp], G[(pp + 1) * SLD + pp + 1], G[pp * SLD + pp + 1], dp, dq);
-          dsc[pp] = dp; dsc[pp + 1] = dq;
-        }
-        bar_all();
-        float2 u[MAXB], v[MAXB], ca[MAXB], cb[MAXB];
-#pragma unroll
-        for (int i = 0; i < MAXB; ++i) {
-          const uchar2 stp = odd ? blk_o[i] : blk_e[i];
-          if (stp.x != 255) {
-            const float* row0 = &G[(2 * stp.x + odd) * SLD + 2 * stp.y + odd];
-            if (odd == 0) {
-              u[i] = *reinterpret_cast<const float2*>(row0);
-              v[i] = *reinterpret_cast<const float2*>(row0 + SLD);
-            } else {
-              u[i] = make_float2(row0[0], row0[1]);
-              v[i] = make_float2(row0[SLD], row0[SLD + 1]);
-            }
-            ca[i] = cs[stp.x];
-            cb[i] = cs[stp.y];
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < MAXB; ++i) {
-          const uchar2 stp = odd ? blk_o[i] : blk_e[i];
-          if (stp.x != 255) {
-            const float2 a = ca[i], bq = cb[i];
-            const float g00 = u[i].x, g01 = u[i].y, g11 = v[i].y;
-            const float g10 = (stp.x == stp.y) ? g01 : v[i].x;            // lower triangle is not stored
-            // rows: (new at ps, new at ps+1) = (g1 + alpha g0, g0 - beta g1)   [scaled rotation, then exchange]
-            const float y00 = fmaf(a.x, g00, g10), y01 = fmaf(a.x, g01, g11);
-            const float y10 = fmaf(a.y, g10, g00), y11 = fmaf(a.y, g11, g01);
-            // columns, same rule
-            float o00 = fmaf(bq.x, y00, y01), o01 = fmaf(bq.y, y01, y00);
-            float o10 = fmaf(bq.x, y10, y11), o11 = fmaf(bq.y, y11, y10);
-            if (stp.x == stp.y) { o01 = 0.f; o10 = 0.f; }
-            float* row0 = &G[(2 * stp.x + odd) * SLD + 2 * stp.y + odd];
-            if (odd == 0) {
-              *reinterpret_cast<float2*>(row0) = make_float2(o00, o01);
-              *reinterpret_cast<float2*>(row0 + SLD) = make_float2(o10, o11);
-            } else {
-              row0[0] = o00; row0[1] = o01; row0[SLD] = o10; row0[SLD + 1] = o11;
-            }
-          }
-        }
-        if (odd && gt < JK - 2) {
-          // positions 0 and JK-1 sit out on odd steps, but row 0 still takes the column rotations and column JK-1
-          // the row rotations of the active pairs
-          const int t = gt < JK / 2 - 1 ? gt : gt - (JK / 2 - 1);
-          const float2 q = cs[t];
-          const int pp = 2 * t + 1;
-          float* e0 = gt < JK / 2 - 1 ? &G[pp] : &G[pp * SLD + JK - 1];
-          float* e1 = gt < JK / 2 - 1 ? e0 + 1 : e0 + SLD;
-          const float g0 = *e0, g1 = *e1;
-          *e0 = fmaf(q.x, g0, g1);
-          *e1 = fmaf(q.y, g1, g0);
-        }
-        bar_all();
-      }
-    }
-    // ---- order the columns by descending norm (de Rijk, whole pair at once)
-    if (gt < JK) diag[gt] = dsc[gt] * dsc[gt] * G[gt * SLD + gt];
-    bar_g();
-    if (gt < JK) {
-      const float d = diag[gt];
-      int rank = 0;
-      for (int j = 0; j < JK; ++j) {
-        const float e = diag[j];
-        rank += (e > d) || (e == d && j < gt);
-      }
-      dest[gt] = rank;
-    }
-    bar_all();
   }
   __syncthreads();
   // ---- re-orthogonalise, write R
@@ -797,6 +852,8 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
   }
   // ASVD_B200_SIMT=1 selects the fp32 SIMT Gram / update kernels (kept as the in-library reference the
   // tensor-core kernels are tested against); default is the tcgen05 path.
+  const char* dbg_env = getenv("ASVD_B200_DBG_STEPS");   // timing experiments only: truncates the inner sweep
+  const int dbg_steps = dbg_env ? atoi(dbg_env) : JK / 2;
   const char* simt_env = getenv("ASVD_B200_SIMT");
   const bool use_tc = !(simt_env && simt_env[0] == '1');
   CUtensorMap tmK, tmMN;
@@ -823,7 +880,7 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
       } else {
         ASVD_LAUNCH(K_GRAM, st, (gram_kernel<<<dim3(p.chunks, p.pairs, p.batch), 256, 0, st>>>(X, xs, p.len_pad, pr, p.len_pad, p.chunks, p.pairs, G, done)));
       }
-      ASVD_LAUNCH(K_SOLVE, st, (solve_kernel<<<dim3(p.pairs, p.batch), SOLVE_THREADS, SOLVE_SMEM, st>>>(G, p.chunks, p.pairs, R, flag, maxoff, status, done, tol, 0)));
+      ASVD_LAUNCH(K_SOLVE, st, (solve_kernel<<<dim3(p.pairs, p.batch), SOLVE_THREADS, SOLVE_SMEM, st>>>(G, p.chunks, p.pairs, R, flag, maxoff, status, done, tol, 0, dbg_steps)));
       if (use_tc) {
         ASVD_LAUNCH(K_UPDATE, st, ASVD_CUDA_CHECK(tc::launch_update_tc(tmMN, X, xs, p.len_pad, pr, p.pairs, p.nv_pad, p.len_pad, p.batch, R, flag, done, st)));
       } else {

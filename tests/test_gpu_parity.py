@@ -307,3 +307,29 @@ def test_full_size_4096_properties():
     sc = scale.cuda()
     kept = ((AB * sc).norm() ** 2).item()
     assert kept == pytest.approx((ref[:r].double() ** 2).sum().item(), rel=1e-4)
+
+
+def test_tensorcore_path_matches_simt_reference(monkeypatch):
+    """The tcgen05 Gram / update kernels (TF32 3-term split) against the fp32 SIMT kernels kept in the library for
+    this purpose (ASVD_B200_SIMT=1): same singular values, same truncated reconstruction."""
+    L = _lib()
+    W, s = O.synthetic_weight(768, 640, seed=21)
+    scale = (s ** 0.5 + 1e-6).float().cuda()
+    tc = L.scaled_svd([W.cuda()], [scale])
+    monkeypatch.setenv("ASVD_B200_SIMT", "1")
+    simt = L.scaled_svd([W.cuda()], [scale])
+    monkeypatch.delenv("ASVD_B200_SIMT")
+    assert tc.status == 0 and simt.status == 0
+    s1, s2 = tc.sigma().double(), simt.sigma().double()
+    assert ((s1 - s2).abs() / (s2 + 1e-3 * s2[0])).max().item() < 2e-5
+    A1, B1 = tc.extract(300, "UV", torch.float32)
+    A2, B2 = simt.extract(300, "UV", torch.float32)
+    rel = ((A1 @ B1 - A2 @ B2) * scale).norm().item() / ((A2 @ B2) * scale).norm().item()
+    assert rel < 5e-4, rel
+
+
+def test_rectangular_llama_shapes_reduced():
+    """Shapes with the aspect ratios of gate/up (tall), down (wide) and lm_head (very tall), scaled down 8x."""
+    for (m, n) in [(1376, 512), (512, 1376), (4000, 512)]:
+        W, s = O.synthetic_weight(m, n, seed=5)
+        check_factorisation(W, (s ** 0.5 + 1e-6).float(), 0.9, "UV")
