@@ -73,6 +73,13 @@ constexpr int JB = 64;        // vectors per block
 constexpr int JK = 2 * JB;    // vectors per pair = order of the Gram / rotation matrices
 constexpr int GRAM_CHUNK = 1024;  // columns of X reduced by one Gram CTA
 
+// X is stored BLOCK-TILED in HBM: tile (blk, ct) = 64 vectors x 32 consecutive elements = one contiguous 8 KB chunk,
+// tiles of a block laid out along the vector dimension.  Every TMA box of the streaming passes is then one
+// contiguous 8 KB read / write (full DRAM pages) instead of 64 separate 128-byte lines 4*len_pad bytes apart.
+__host__ __device__ inline int64_t xt_off(int vec, int col, int nct) {
+  return ((int64_t)((vec >> 6) * nct + (col >> 5)) << 11) + ((vec & 63) << 5) + (col & 31);
+}
+
 struct SvdPlan {
   int m, n, batch;
   int tall;        // 1: m >= n, vectors are columns of W*s (length m); 0: vectors are rows (length n)
@@ -82,7 +89,7 @@ struct SvdPlan {
   int ldy;         // leading dimension of Y rows (length nv, padded to 4)
   int nb, rounds, pairs, chunks;
   // byte offsets into the workspace
-  size_t off_ptrs, off_pairs, off_X, off_Y, off_G, off_R, off_flag, off_maxoff, off_done, off_sigma, off_perm,
+  size_t off_ptrs, off_pairs, off_X, off_Xr, off_Y, off_G, off_R, off_flag, off_maxoff, off_done, off_sigma, off_perm,
       off_status, off_scale, off_norm;
   size_t bytes;
 };

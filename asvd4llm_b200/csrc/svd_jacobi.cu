@@ -93,7 +93,8 @@ SvdPlan make_plan(int m, int n, int batch) {
   auto take = [&](size_t bytes) { size_t o = off; off = (size_t)round_up((int64_t)(off + bytes), 256); return o; };
   p.off_ptrs = take(sizeof(void*) * 2 * (size_t)batch);
   p.off_pairs = take(sizeof(int2) * (size_t)p.rounds * p.pairs);
-  p.off_X = take(sizeof(float) * (size_t)batch * p.nv_pad * p.len_pad);
+  p.off_X = take(sizeof(float) * (size_t)batch * p.nv_pad * p.len_pad);    // block-tiled (xt_off), the Jacobi working set
+  p.off_Xr = take(sizeof(float) * (size_t)batch * p.nv_pad * p.len_pad);   // row-major copy made once after convergence
   p.off_Y = take(sizeof(float) * (size_t)batch * p.nv_pad * p.ldy);
   p.off_G = take(sizeof(float) * (size_t)batch * p.pairs * p.chunks * JK * JK);
   p.off_R = take(sizeof(float) * (size_t)batch * p.pairs * JK * JK);
@@ -130,12 +131,12 @@ __global__ void __launch_bounds__(256) prep_kernel(const void* const* __restrict
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {
       int j = j0 + r, i = i0 + tx;
-      if (j < n && i < m) Xb[(int64_t)j * ldx + i] = tile[tx][r];
+      if (j < n && i < m) Xb[xt_off(j, i, ldx >> 5)] = tile[tx][r];
     }
   } else {
     for (int r = ty; r < 32; r += 8) {
       int i = i0 + r, j = j0 + tx;
-      if (i < m && j < n) Xb[(int64_t)i * ldx + j] = to_f32<T>(W[(int64_t)i * ldw + j]) * s[j];
+      if (i < m && j < n) Xb[xt_off(i, j, ldx >> 5)] = to_f32<T>(W[(int64_t)i * ldw + j]) * s[j];
     }
   }
 }
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, 
   const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
   const int row = t >> 1, kq = (t & 1) * 8;
   const int vec = (row < JB) ? pr.x * JB + row : pr.y * JB + (row - JB);
-  const float* src = Xb + (int64_t)vec * ldx;
+  const int nct = ldx >> 5;
   const int kbeg = c * GRAM_CHUNK, kend = min(len_pad, kbeg + GRAM_CHUNK);
   const int nk = (kend - kbeg) / GK;
 
@@ -171,8 +172,9 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, 
 
   float4 r0, r1;
   auto gload = [&](int k0) {
-    r0 = *reinterpret_cast<const float4*>(src + k0 + kq);
-    r1 = *reinterpret_cast<const float4*>(src + k0 + kq + 4);
+    const float* src = Xb + xt_off(vec, k0 + kq, nct);
+    r0 = *reinterpret_cast<const float4*>(src);
+    r1 = *reinterpret_cast<const float4*>(src + 4);
   };
   auto sstore = [&](int buf) {
     As[buf][kq + 0][row] = r0.x; As[buf][kq + 1][row] = r0.y; As[buf][kq + 2][row] = r0.z; As[buf][kq + 3][row] = r0.w;
@@ -284,6 +286,7 @@ solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, flo
   const int tid = threadIdx.x;
   const float* Gp = Gpart + (int64_t)idx * chunks * (JK * JK);
 
+#pragma unroll 4
   for (int e = tid; e < JK * JK; e += SOLVE_THREADS) {
     float s = 0.f;
     int c = 0;
@@ -379,48 +382,58 @@ solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, flo
       bar_all();           // gd / go visible
       bar_all();           // cs / dsc written by the parameter threads
       if (dbg_mode & 2) continue;
+      // the parameters of this patch's four row pairs and four column pairs (32 contiguous bytes each)
+      float2 qr[4], qc[4];
+      {
+        const float4 r0 = *reinterpret_cast<const float4*>(&cs[4 * pa]), r1 = *reinterpret_cast<const float4*>(&cs[4 * pa + 2]);
+        const float4 c0 = *reinterpret_cast<const float4*>(&cs[4 * pc]), c1 = *reinterpret_cast<const float4*>(&cs[4 * pc + 2]);
+        qr[0] = make_float2(r0.x, r0.y); qr[1] = make_float2(r0.z, r0.w); qr[2] = make_float2(r1.x, r1.y); qr[3] = make_float2(r1.z, r1.w);
+        qc[0] = make_float2(c0.x, c0.y); qc[1] = make_float2(c0.z, c0.w); qc[2] = make_float2(c1.x, c1.y); qc[3] = make_float2(c1.z, c1.w);
+      }
       if (!odd) {
 #pragma unroll
         for (int lp = 0; lp < 4; ++lp) {                 // rows (2lp, 2lp+1): new = (g1 + alpha g0, g0 - beta g1)
-          const float2 q = cs[4 * pa + lp];
+          const float2 q = qr[lp];
 #pragma unroll
           for (int j = 0; j < 8; ++j) ASVD_ROT_SWAP(g[2 * lp][j], g[2 * lp + 1][j], q);
         }
 #pragma unroll
         for (int lp = 0; lp < 4; ++lp) {                 // columns, same rule
-          const float2 q = cs[4 * pc + lp];
+          const float2 q = qc[lp];
 #pragma unroll
           for (int i = 0; i < 8; ++i) ASVD_ROT_SWAP(g[i][2 * lp], g[i][2 * lp + 1], q);
         }
       } else {
         // rows: exchange the boundary rows with the patches above / below
-        *reinterpret_cast<float4*>(&rowF[pa * JK + 8 * pc]) = make_float4(g[0][0], g[0][1], g[0][2], g[0][3]);
-        *reinterpret_cast<float4*>(&rowF[pa * JK + 8 * pc + 4]) = make_float4(g[0][4], g[0][5], g[0][6], g[0][7]);
-        *reinterpret_cast<float4*>(&rowL[pa * JK + 8 * pc]) = make_float4(g[7][0], g[7][1], g[7][2], g[7][3]);
-        *reinterpret_cast<float4*>(&rowL[pa * JK + 8 * pc + 4]) = make_float4(g[7][4], g[7][5], g[7][6], g[7][7]);
+        // exchange layout: [patch row][half of the 8 values][patch column][4 values] -> the 16 lanes that share a patch
+        // row touch 256 contiguous bytes per access (no bank conflicts)
+        *reinterpret_cast<float4*>(&rowF[pa * JK + 4 * pc]) = make_float4(g[0][0], g[0][1], g[0][2], g[0][3]);
+        *reinterpret_cast<float4*>(&rowF[pa * JK + 64 + 4 * pc]) = make_float4(g[0][4], g[0][5], g[0][6], g[0][7]);
+        *reinterpret_cast<float4*>(&rowL[pa * JK + 4 * pc]) = make_float4(g[7][0], g[7][1], g[7][2], g[7][3]);
+        *reinterpret_cast<float4*>(&rowL[pa * JK + 64 + 4 * pc]) = make_float4(g[7][4], g[7][5], g[7][6], g[7][7]);
         bar_g();
         {
           float below[8], above[8];
           if (pa < 15) {
-            const float4 x0 = *reinterpret_cast<const float4*>(&rowF[(pa + 1) * JK + 8 * pc]);
-            const float4 x1 = *reinterpret_cast<const float4*>(&rowF[(pa + 1) * JK + 8 * pc + 4]);
+            const float4 x0 = *reinterpret_cast<const float4*>(&rowF[(pa + 1) * JK + 4 * pc]);
+            const float4 x1 = *reinterpret_cast<const float4*>(&rowF[(pa + 1) * JK + 64 + 4 * pc]);
             below[0] = x0.x; below[1] = x0.y; below[2] = x0.z; below[3] = x0.w;
             below[4] = x1.x; below[5] = x1.y; below[6] = x1.z; below[7] = x1.w;
           }
           if (pa > 0) {
-            const float4 x0 = *reinterpret_cast<const float4*>(&rowL[(pa - 1) * JK + 8 * pc]);
-            const float4 x1 = *reinterpret_cast<const float4*>(&rowL[(pa - 1) * JK + 8 * pc + 4]);
+            const float4 x0 = *reinterpret_cast<const float4*>(&rowL[(pa - 1) * JK + 4 * pc]);
+            const float4 x1 = *reinterpret_cast<const float4*>(&rowL[(pa - 1) * JK + 64 + 4 * pc]);
             above[0] = x0.x; above[1] = x0.y; above[2] = x0.z; above[3] = x0.w;
             above[4] = x1.x; above[5] = x1.y; above[6] = x1.z; above[7] = x1.w;
           }
 #pragma unroll
           for (int lp = 0; lp < 3; ++lp) {               // rows (2lp+1, 2lp+2), pair index 4pa + lp
-            const float2 q = cs[4 * pa + lp];
+            const float2 q = qr[lp];
 #pragma unroll
             for (int j = 0; j < 8; ++j) ASVD_ROT_SWAP(g[2 * lp + 1][j], g[2 * lp + 2][j], q);
           }
           if (pa < 15) {                                 // row 8pa+7 is the p side of pair 4pa+3: new = below + alpha own
-            const float2 q = cs[4 * pa + 3];
+            const float2 q = qr[3];
 #pragma unroll
             for (int j = 0; j < 8; ++j) g[7][j] = fmaf(q.x, g[7][j], below[j]);
           }
@@ -431,33 +444,33 @@ solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, flo
           }
         }
         // columns: exchange the (row-rotated) boundary columns with the patches left / right
-        *reinterpret_cast<float4*>(&colF[pc * JK + 8 * pa]) = make_float4(g[0][0], g[1][0], g[2][0], g[3][0]);
-        *reinterpret_cast<float4*>(&colF[pc * JK + 8 * pa + 4]) = make_float4(g[4][0], g[5][0], g[6][0], g[7][0]);
-        *reinterpret_cast<float4*>(&colL[pc * JK + 8 * pa]) = make_float4(g[0][7], g[1][7], g[2][7], g[3][7]);
-        *reinterpret_cast<float4*>(&colL[pc * JK + 8 * pa + 4]) = make_float4(g[4][7], g[5][7], g[6][7], g[7][7]);
+        *reinterpret_cast<float4*>(&colF[pa * JK + 4 * pc]) = make_float4(g[0][0], g[1][0], g[2][0], g[3][0]);
+        *reinterpret_cast<float4*>(&colF[pa * JK + 64 + 4 * pc]) = make_float4(g[4][0], g[5][0], g[6][0], g[7][0]);
+        *reinterpret_cast<float4*>(&colL[pa * JK + 4 * pc]) = make_float4(g[0][7], g[1][7], g[2][7], g[3][7]);
+        *reinterpret_cast<float4*>(&colL[pa * JK + 64 + 4 * pc]) = make_float4(g[4][7], g[5][7], g[6][7], g[7][7]);
         bar_g();
         {
           float right[8], left[8];
           if (pc < 15) {
-            const float4 x0 = *reinterpret_cast<const float4*>(&colF[(pc + 1) * JK + 8 * pa]);
-            const float4 x1 = *reinterpret_cast<const float4*>(&colF[(pc + 1) * JK + 8 * pa + 4]);
+            const float4 x0 = *reinterpret_cast<const float4*>(&colF[pa * JK + 4 * (pc + 1)]);
+            const float4 x1 = *reinterpret_cast<const float4*>(&colF[pa * JK + 64 + 4 * (pc + 1)]);
             right[0] = x0.x; right[1] = x0.y; right[2] = x0.z; right[3] = x0.w;
             right[4] = x1.x; right[5] = x1.y; right[6] = x1.z; right[7] = x1.w;
           }
           if (pc > 0) {
-            const float4 x0 = *reinterpret_cast<const float4*>(&colL[(pc - 1) * JK + 8 * pa]);
-            const float4 x1 = *reinterpret_cast<const float4*>(&colL[(pc - 1) * JK + 8 * pa + 4]);
+            const float4 x0 = *reinterpret_cast<const float4*>(&colL[pa * JK + 4 * (pc - 1)]);
+            const float4 x1 = *reinterpret_cast<const float4*>(&colL[pa * JK + 64 + 4 * (pc - 1)]);
             left[0] = x0.x; left[1] = x0.y; left[2] = x0.z; left[3] = x0.w;
             left[4] = x1.x; left[5] = x1.y; left[6] = x1.z; left[7] = x1.w;
           }
 #pragma unroll
           for (int lp = 0; lp < 3; ++lp) {
-            const float2 q = cs[4 * pc + lp];
+            const float2 q = qc[lp];
 #pragma unroll
             for (int i = 0; i < 8; ++i) ASVD_ROT_SWAP(g[i][2 * lp + 1], g[i][2 * lp + 2], q);
           }
           if (pc < 15) {
-            const float2 q = cs[4 * pc + 3];
+            const float2 q = qc[3];
 #pragma unroll
             for (int i = 0; i < 8; ++i) g[i][7] = fmaf(q.x, g[i][7], right[i]);
           }
@@ -541,56 +554,71 @@ solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, flo
   }
   __syncthreads();
   // ---- re-orthogonalise, write R
+  // 8x8 register tiles (rows {4ta..} U {64+4ta..}, columns {4tb..} U {64+4tb..}) on the first 256 threads: 64 FMAs
+  // per 4-10 shared-memory loads, so both 128^3 products run at the FMA issue rate
   float* E = G;
-  for (int tile = tid; tile < (JK / 4) * (JK / 4); tile += SOLVE_THREADS) {
-    const int ta = tile >> 5, tb = tile & 31;
-    float e[4][4];
+  const int ta = (tid >> 4) & 15, tb = tid & 15;
+  if (tid < 256) {
+    float e[8][8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) e[i][j] = 0.f;
+      for (int j = 0; j < 8; ++j) e[i][j] = 0.f;
+#pragma unroll 2
     for (int l = 0; l < JK; ++l) {
-      float4 a = *reinterpret_cast<const float4*>(&Rs[l * SLD + ta * 4]);
-      float4 bb = *reinterpret_cast<const float4*>(&Rs[l * SLD + tb * 4]);
-      float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+      const float4 a0 = *reinterpret_cast<const float4*>(&Rs[l * SLD + ta * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&Rs[l * SLD + 64 + ta * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Rs[l * SLD + tb * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Rs[l * SLD + 64 + tb * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) e[i][j] = fmaf(av[i], bv[j], e[i][j]);
+        for (int j = 0; j < 8; ++j) e[i][j] = fmaf(av[i], bv[j], e[i][j]);
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      *reinterpret_cast<float4*>(&E[(ta * 4 + i) * SLD + tb * 4]) = make_float4(e[i][0], e[i][1], e[i][2], e[i][3]);
+    for (int i = 0; i < 8; ++i) {
+      const int rr = (i < 4) ? ta * 4 + i : 64 + ta * 4 + (i - 4);
+      *reinterpret_cast<float4*>(&E[rr * SLD + tb * 4]) = make_float4(e[i][0], e[i][1], e[i][2], e[i][3]);
+      *reinterpret_cast<float4*>(&E[rr * SLD + 64 + tb * 4]) = make_float4(e[i][4], e[i][5], e[i][6], e[i][7]);
+    }
   }
   __syncthreads();
-  float* Ro = Rout + (int64_t)idx * (JK * JK);
-  for (int tile = tid; tile < (JK / 4) * (JK / 4); tile += SOLVE_THREADS) {
-    const int ta = tile >> 5, tb = tile & 31;
-    float o[4][4];
+  if (tid < 256) {
+    float o[8][8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+      for (int j = 0; j < 8; ++j) o[i][j] = 0.f;
+    const float* ra = &Rs[(ta * 4) * SLD];
+    const float* rb = &Rs[(64 + ta * 4) * SLD];
+#pragma unroll 2
     for (int l = 0; l < JK; ++l) {
-      float4 bb = *reinterpret_cast<const float4*>(&E[l * SLD + tb * 4]);
-      float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+      const float4 b0 = *reinterpret_cast<const float4*>(&E[l * SLD + tb * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&E[l * SLD + 64 + tb * 4]);
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const float av[8] = {ra[l], ra[SLD + l], ra[2 * SLD + l], ra[3 * SLD + l], rb[l], rb[SLD + l], rb[2 * SLD + l], rb[3 * SLD + l]};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float a = Rs[(ta * 4 + i) * SLD + l];
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o[i][j] = fmaf(a, bv[j], o[i][j]);
-      }
+        for (int j = 0; j < 8; ++j) o[i][j] = fmaf(av[i], bv[j], o[i][j]);
     }
+    float* Ro = Rout + (int64_t)idx * (JK * JK);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float4 rr = *reinterpret_cast<const float4*>(&Rs[(ta * 4 + i) * SLD + tb * 4]);
-      const float4 w = make_float4(1.5f * rr.x - 0.5f * o[i][0], 1.5f * rr.y - 0.5f * o[i][1], 1.5f * rr.z - 0.5f * o[i][2],
-                                   1.5f * rr.w - 0.5f * o[i][3]);
-      if (!transpose_out) {
-        *reinterpret_cast<float4*>(&Ro[(ta * 4 + i) * JK + tb * 4]) = w;
-      } else {                      // R^T for the tensor-core update (A operand, K-major)
-        Ro[(tb * 4 + 0) * JK + ta * 4 + i] = w.x; Ro[(tb * 4 + 1) * JK + ta * 4 + i] = w.y;
-        Ro[(tb * 4 + 2) * JK + ta * 4 + i] = w.z; Ro[(tb * 4 + 3) * JK + ta * 4 + i] = w.w;
+    for (int i = 0; i < 8; ++i) {
+      const int rr = (i < 4) ? ta * 4 + i : 64 + ta * 4 + (i - 4);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int cc = hh * 64 + tb * 4;
+        const float4 x = *reinterpret_cast<const float4*>(&Rs[rr * SLD + cc]);
+        const float4 w = make_float4(1.5f * x.x - 0.5f * o[i][4 * hh], 1.5f * x.y - 0.5f * o[i][4 * hh + 1],
+                                     1.5f * x.z - 0.5f * o[i][4 * hh + 2], 1.5f * x.w - 0.5f * o[i][4 * hh + 3]);
+        if (!transpose_out) {
+          *reinterpret_cast<float4*>(&Ro[rr * JK + cc]) = w;
+        } else {
+          Ro[(cc + 0) * JK + rr] = w.x; Ro[(cc + 1) * JK + rr] = w.y; Ro[(cc + 2) * JK + rr] = w.z; Ro[(cc + 3) * JK + rr] = w.w;
+        }
       }
     }
   }
@@ -632,7 +660,7 @@ update_kernel(float* __restrict__ X, int64_t mat_stride, int ldx, const int2* __
       int e = t + 256 * i;
       int row = e >> 5, c4 = (e & 31) * 4;
       int vec = (row < JB) ? pr.x * JB + row : pr.y * JB + (row - JB);
-      cp_async16(&Xs[(buf * JK + row) * 128 + c4], Xb + (int64_t)vec * ldx + c0 + c4);
+      cp_async16(&Xs[(buf * JK + row) * 128 + c4], Xb + xt_off(vec, c0 + c4, ldx >> 5));
     }
   };
   {
@@ -675,15 +703,24 @@ update_kernel(float* __restrict__ X, int64_t mat_stride, int ldx, const int2* __
     for (int r = 0; r < 8; ++r) {
       int j = (r < 4) ? ty * 4 + r : 64 + ty * 4 + (r - 4);
       int vec = (j < JB) ? pr.x * JB + j : pr.y * JB + (j - JB);
-      float* dst = Xb + (int64_t)vec * ldx + c0;
-      *reinterpret_cast<float4*>(dst + tx * 4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-      *reinterpret_cast<float4*>(dst + 64 + tx * 4) = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
+      *reinterpret_cast<float4*>(Xb + xt_off(vec, c0 + tx * 4, ldx >> 5)) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+      *reinterpret_cast<float4*>(Xb + xt_off(vec, c0 + 64 + tx * 4, ldx >> 5)) = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
     }
     __syncthreads();
   }
 }
 
 // ------------------------------------------------------------------------------------------------ finalize
+// block-tiled X -> row-major copy (once per factorisation; the epilogue kernels below read rows)
+__global__ void __launch_bounds__(256) untile_kernel(const float* __restrict__ Xt, float* __restrict__ Xr, int64_t mat_stride,
+                                                     int nv_pad, int ld) {
+  const int b = blockIdx.z, vec = blockIdx.y;
+  const int col4 = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (col4 >= ld) return;
+  const float4 v = *reinterpret_cast<const float4*>(Xt + b * mat_stride + xt_off(vec, col4, ld >> 5));
+  *reinterpret_cast<float4*>(Xr + b * mat_stride + (int64_t)vec * ld + col4) = v;
+}
+
 // per-row 2-norm; optionally normalises the row in place.  One CTA per row.
 // `anchor` (optional): the Jacobi column norm of the same vector.  |Y_j| recomputed from the original weight is
 // free of accumulated rotation drift but, for sigma_j below ~eps*sigma_max, it is dominated by leakage from the
@@ -821,6 +858,7 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
   const void* const* d_W = reinterpret_cast<const void* const*>(ws + p.off_ptrs);
   const int2* d_pairs = reinterpret_cast<const int2*>(ws + p.off_pairs);
   float* X = reinterpret_cast<float*>(ws + p.off_X);
+  float* Xr = reinterpret_cast<float*>(ws + p.off_Xr);
   float* Y = reinterpret_cast<float*>(ws + p.off_Y);
   float* G = reinterpret_cast<float*>(ws + p.off_G);
   float* R = reinterpret_cast<float*>(ws + p.off_R);
@@ -909,7 +947,8 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
       ASVD_CUDA_CHECK(cudaMemcpyAsync(done, h_done.data(), sizeof(int) * p.batch, cudaMemcpyHostToDevice, st));
   }
   // rows of X are sigma_j u_j: normalise, recover the other factor from the original weight, anchor sigma to it
-  ASVD_LAUNCH(K_FINAL, st, (rownorm_kernel<<<dim3(p.nv_pad, p.batch), 256, 0, st>>>(X, xs, p.len_pad, p.len_pad, 1, sigma, p.nv_pad, status, nullptr)));
+  ASVD_LAUNCH(K_FINAL, st, (untile_kernel<<<dim3((p.len_pad / 4 + 255) / 256, p.nv_pad, p.batch), 256, 0, st>>>(X, Xr, xs, p.nv_pad, p.len_pad)));
+  ASVD_LAUNCH(K_FINAL, st, (rownorm_kernel<<<dim3(p.nv_pad, p.batch), 256, 0, st>>>(Xr, xs, p.len_pad, p.len_pad, 1, sigma, p.nv_pad, status, nullptr)));
   ASVD_CUDA_CHECK(cudaGetLastError());
   {
     GemmBatch gb;
@@ -927,10 +966,10 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
       cudaError_t e;
       prof_begin(K_FINAL, st);
       if (p.tall)   // Y[j][l] = sum_i Xhat[j][i] W[i][l] * s[l]
-        e = launch_gemm128<float, T, float, true>(X + b * xs, p.len_pad, (const T*)nullptr, ldw, Y + b * gb.strideC, p.ldy,
+        e = launch_gemm128<float, T, float, true>(Xr + b * xs, p.len_pad, (const T*)nullptr, ldw, Y + b * gb.strideC, p.ldy,
                                                   p.nv_pad, p.n, p.m, nullptr, sb, nullptr, 1, g1, st);
       else          // Y[j][i] = sum_l Xhat[j][l] s[l] W[i][l]
-        e = launch_gemm128<float, T, float, false>(X + b * xs, p.len_pad, (const T*)nullptr, ldw, Y + b * gb.strideC, p.ldy,
+        e = launch_gemm128<float, T, float, false>(Xr + b * xs, p.len_pad, (const T*)nullptr, ldw, Y + b * gb.strideC, p.ldy,
                                                    p.nv_pad, p.m, p.n, sb, nullptr, nullptr, 1, g1, st);
       prof_end(K_FINAL, st);
       ASVD_CUDA_CHECK(e);
@@ -962,7 +1001,7 @@ using namespace asvd;
 template <typename TC>
 static int do_extract(const SvdPlan& p, const unsigned char* ws, int b, int r, int fuse, TC* A, int64_t lda, TC* B,
                       int64_t ldb, cudaStream_t st) {
-  const float* X = reinterpret_cast<const float*>(ws + p.off_X) + (int64_t)b * p.nv_pad * p.len_pad;
+  const float* X = reinterpret_cast<const float*>(ws + p.off_Xr) + (int64_t)b * p.nv_pad * p.len_pad;   // row-major copy
   const float* Y = reinterpret_cast<const float*>(ws + p.off_Y) + (int64_t)b * p.nv_pad * p.ldy;
   const float* sigma = reinterpret_cast<const float*>(ws + p.off_sigma) + (int64_t)b * p.nv_pad;
   const int* perm = reinterpret_cast<const int*>(ws + p.off_perm) + (int64_t)b * p.nv_pad;

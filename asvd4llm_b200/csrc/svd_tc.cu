@@ -13,6 +13,7 @@
 //   warps 4-7  epilogue: tcgen05.ld -> global partial Gram
 //   warps 8-11 split: hi/lo rewrite of the landed tile, fence.proxy.async, arrive
 #include <type_traits>
+#include <stdlib.h>
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -91,8 +92,10 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__
           mbar_wait(&empty[hs], hph ^ 1);
           unsigned char* hi = smem + hs * GR_HI_BYTES;
           mbar_arrive_expect_tx(&full[hs], GR_HI_BYTES);
-          tma_load_2d(hi, &tmX, &full[hs], k, b * nv_pad + pr.x * JB);
-          tma_load_2d(hi + GR_HI_BYTES / 2, &tmX, &full[hs], k, b * nv_pad + pr.y * JB);
+          // block-tiled X: tile (block, k/32) is one contiguous 8 KB chunk = rows [tile*64, tile*64+64) of a [.., 32] view
+          const int nb = nv_pad / JB, nct = len_pad >> 5;
+          tma_load_2d(hi, &tmX, &full[hs], 0, ((b * nb + pr.x) * nct + (k >> 5)) * JB);
+          tma_load_2d(hi + GR_HI_BYTES / 2, &tmX, &full[hs], 0, ((b * nb + pr.y) * nct + (k >> 5)) * JB);
           if (++hs == GR_NH) { hs = 0; hph ^= 1; }
         }
       }
@@ -212,7 +215,7 @@ constexpr uint32_t UP_TMEM_A_HI = 256, UP_TMEM_A_LO = 384;   // column offsets; 
 __global__ void __launch_bounds__(UP_THREADS, 1)
 update_tc_kernel(const __grid_constant__ CUtensorMap tmX, float* __restrict__ X, int64_t mat_stride, int ldx,
                  const int2* __restrict__ pairs, int pairs_per_mat, int nv_pad, int tiles_total, int tiles_per_cta,
-                 const float* __restrict__ R, const int* __restrict__ pairflag, const int* __restrict__ done) {
+                 const float* __restrict__ R, const int* __restrict__ pairflag, const int* __restrict__ done, int dbg) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + UP_BAR_OFFSET);
@@ -232,6 +235,7 @@ update_tc_kernel(const __grid_constant__ CUtensorMap tmX, float* __restrict__ X,
   const int2 pr = pairs[p];
   const int tile0 = blockIdx.x * tiles_per_cta;
   const int ntiles = min(tiles_per_cta, tiles_total - tile0);
+  const int nb = nv_pad / JB, nct = tiles_total * (UP_TN / 32);
 
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tmX);
   if (warp == 1 && lane == 0) {
@@ -257,8 +261,8 @@ update_tc_kernel(const __grid_constant__ CUtensorMap tmX, float* __restrict__ X,
         mbar_arrive_expect_tx(&full[stage], UP_HI_BYTES);
         // box = 64 rows x 32 floats; rows 0-63 of the tile are block I, rows 64-127 block J; two 32-column groups
         for (int g = 0; g < 2; ++g) {
-          tma_load_2d(hi + g * 16384, &tmX, &full[stage], c0 + g * 32, b * nv_pad + pr.x * JB);
-          tma_load_2d(hi + g * 16384 + 8192, &tmX, &full[stage], c0 + g * 32, b * nv_pad + pr.y * JB);
+          tma_load_2d(hi + g * 16384, &tmX, &full[stage], 0, ((b * nb + pr.x) * nct + (c0 >> 5) + g) * JB);
+          tma_load_2d(hi + g * 16384 + 8192, &tmX, &full[stage], 0, ((b * nb + pr.y) * nct + (c0 >> 5) + g) * JB);
         }
         if (++stage == UP_NH) { stage = 0; phase ^= 1; }
       }
@@ -284,8 +288,10 @@ update_tc_kernel(const __grid_constant__ CUtensorMap tmX, float* __restrict__ X,
           const uint64_t bh = make_desc_mnmajor_sw128_32b(hi_addr + k * 1024, 16384);
           const uint64_t bl = make_desc_mnmajor_sw128_32b(lo_addr + k * 1024, 16384);
           mma_tf32_ts(d_tmem, tmem_base + UP_TMEM_A_HI + k * 8, bh, idesc, k ? 1u : 0u);
-          mma_tf32_ts(d_tmem, tmem_base + UP_TMEM_A_LO + k * 8, bh, idesc, 1u);
-          mma_tf32_ts(d_tmem, tmem_base + UP_TMEM_A_HI + k * 8, bl, idesc, 1u);
+          if (!(dbg & 2)) {
+            mma_tf32_ts(d_tmem, tmem_base + UP_TMEM_A_LO + k * 8, bh, idesc, 1u);
+            mma_tf32_ts(d_tmem, tmem_base + UP_TMEM_A_HI + k * 8, bl, idesc, 1u);
+          }
         }
         tc_commit(&lo_empty[ls]);
         tc_commit(&tfull[buf]);          // the hi slot is handed to the epilogue, which overwrites it with D
@@ -332,6 +338,7 @@ update_tc_kernel(const __grid_constant__ CUtensorMap tmX, float* __restrict__ X,
       unsigned char* slot = smem + stage * UP_HI_BYTES;
 #pragma unroll
       for (int g = 0; g < UP_TN / 32; ++g) {
+        if (dbg & 4) break;
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * UP_TN + g * 32), v);
         tmem_ld_wait();
@@ -352,9 +359,9 @@ update_tc_kernel(const __grid_constant__ CUtensorMap tmX, float* __restrict__ X,
       asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps
       if (warp == 4 && lane == 0) {
         const int c0 = (tile0 + t) * UP_TN;
-        for (int g = 0; g < 2; ++g) {
-          tma_store_2d(&tmX, slot + g * 16384, c0 + g * 32, b * nv_pad + pr.x * JB);
-          tma_store_2d(&tmX, slot + g * 16384 + 8192, c0 + g * 32, b * nv_pad + pr.y * JB);
+        for (int g = 0; g < ((dbg & 8) ? 0 : 2); ++g) {
+          tma_store_2d(&tmX, slot + g * 16384, 0, ((b * nb + pr.x) * nct + (c0 >> 5) + g) * JB);
+          tma_store_2d(&tmX, slot + g * 16384 + 8192, 0, ((b * nb + pr.y) * nct + (c0 >> 5) + g) * JB);
         }
         tma_store_commit();
         if (pending_stage >= 0) {                              // previous tile's store has finished reading its slot
@@ -378,8 +385,10 @@ update_tc_kernel(const __grid_constant__ CUtensorMap tmX, float* __restrict__ X,
       mbar_wait(&lo_empty[ls], lph ^ 1);
       float4* hi = reinterpret_cast<float4*>(smem + stage * UP_HI_BYTES);
       float4* lo = reinterpret_cast<float4*>(smem + UP_LO_OFFSET + ls * UP_HI_BYTES);
-      split_tile(hi, lo, t128);
-      split_tile(hi + 1024, lo + 1024, t128);
+      if (!(dbg & 1)) {
+        split_tile(hi, lo, t128);
+        split_tile(hi + 1024, lo + 1024, t128);
+      }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&lo_ready[ls]);
@@ -403,10 +412,10 @@ static int sm_count() {
   return g_sms;
 }
 
-// tensor map over X of the whole batch: [batch * nv_pad rows, len_pad cols] fp32, box 64 rows x 32 floats
+// tensor map over the block-tiled X of the whole batch, viewed as [batch * nv_pad * len_pad / 32 rows, 32 cols] fp32:
+// a box of 64 rows x 32 floats is exactly one contiguous 8 KB tile
 bool make_x_tmap(CUtensorMap* map, const float* X, int batch, int nv_pad, int len_pad) {
-  return make_tmap_2d(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, X, (uint64_t)batch * nv_pad, (uint64_t)len_pad, (uint64_t)len_pad,
-                      64, 32);
+  return make_tmap_2d(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, X, (uint64_t)batch * nv_pad * (len_pad / 32), 32, 32, 64, 32);
 }
 
 cudaError_t launch_gram_tc(const CUtensorMap& tmX, const int2* pairs, int pairs_per_mat, int chunks, int chunk_cols,
@@ -427,8 +436,8 @@ cudaError_t launch_gram_tc(const CUtensorMap& tmX, const int2* pairs, int pairs_
 
 // tensor map for the update: same matrix, box 64 rows x 32 floats, 128B swizzle with 32-byte atoms (MN-major operand)
 bool make_x_tmap_mn(CUtensorMap* map, const float* X, int batch, int nv_pad, int len_pad) {
-  return make_tmap_2d(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, X, (uint64_t)batch * nv_pad, (uint64_t)len_pad, (uint64_t)len_pad,
-                      64, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  return make_tmap_2d(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, X, (uint64_t)batch * nv_pad * (len_pad / 32), 32, 32, 64, 32,
+                      CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
 }
 
 cudaError_t launch_update_tc(const CUtensorMap& tmX, float* X, int64_t mat_stride, int ldx, const int2* pairs,
@@ -440,15 +449,19 @@ cudaError_t launch_update_tc(const CUtensorMap& tmX, float* X, int64_t mat_strid
     if (e != cudaSuccess) return e;
     attr = true;
   }
+  const char* dbg_env = getenv("ASVD_B200_DBG_UPDATE");      // timing experiments only
+  const int dbg = dbg_env ? atoi(dbg_env) : 0;
   const int tiles_total = len_pad / UP_TN;
-  // aim for ~3 waves of CTAs so the one-off R^T load into tensor memory is amortised over >= 8 tiles
-  int ctas_x = (3 * sm_count() + pairs_per_mat * batch - 1) / (pairs_per_mat * batch);
+  // One wave of CTAs: every CTA pays a fixed ~15 us (TMEM allocation, gathering R^T into tensor memory, pipeline fill
+  // and drain), so a pair's column range is split only as far as needed to occupy the SMs once.
+  int ctas_x = sm_count() / (pairs_per_mat * batch);
+  if (ctas_x < 1) ctas_x = 1;
   int tiles_per_cta = (tiles_total + ctas_x - 1) / ctas_x;
-  if (tiles_per_cta < 8) tiles_per_cta = tiles_total < 8 ? tiles_total : 8;
+  if (tiles_per_cta < 4) tiles_per_cta = tiles_total < 4 ? tiles_total : 4;
   ctas_x = (tiles_total + tiles_per_cta - 1) / tiles_per_cta;
   update_tc_kernel<<<dim3(ctas_x, pairs_per_mat, batch), UP_THREADS, UP_SMEM, st>>>(tmX, X, mat_stride, ldx, pairs, pairs_per_mat,
                                                                                   nv_pad, tiles_total, tiles_per_cta, R,
-                                                                                  pairflag, done);
+                                                                                  pairflag, done, dbg);
   return cudaGetLastError();
 }
 
