@@ -224,37 +224,55 @@ def main():
     h2d = B * (M * N_IN * 2 + N_IN * 2)
     d2h = B * (r * (M + N_IN) * 2)
 
-    # ---- roofline of the dominant kernel: per-class CUDA-event timing over the first sweeps (every pair active)
+    # ---- roofline.  The SVD "kernel" of SURVEY.md 8(d) is the Jacobi round: one launch each of gram_tc_kernel,
+    # solve_kernel and update_tc_kernel; its algorithmic HBM bytes are one read of X (Gram), one read + one write
+    # of X (update) plus the small Gram / rotation buffers.  Timed with per-class CUDA events (asvd_profile_*)
+    # over the first two sweeps, where every block pair is active; per-kernel figures are reported beside it.
     roofline, classes = None, None
     if rank == 0:
-        _lib.profile_enable(True)
         Ws, sdm = pools[0]
         scales = [_lib.scaling_vector(s, None, ALPHA, N_IN, dev) for s in sdm]
+        _lib.profile_enable(True)
         before = _lib.profile_read()
         _lib.scaled_svd(Ws, scales, max_sweeps=2)
         torch.cuda.synchronize()
         after = _lib.profile_read()
-        _lib.profile_enable(False)
         classes = {k: {"ms": after[k][0], "launches": after[k][1] - before[k][1]} for k in after if after[k][1] > before[k][1]}
-        dom = max(("gram", "solve", "update"), key=lambda k: classes.get(k, {"ms": 0})["ms"])
+        _lib.profile_enable(True)                       # resets the timers
+        before = _lib.profile_read()
+        _lib.scaled_svd(Ws, scales)
+        torch.cuda.synchronize()
+        after = _lib.profile_read()
+        _lib.profile_enable(False)
+        full_run = {k: round(after[k][0], 2) for k in after if after[k][1] > before[k][1]}
         nv = len_ = 4096
-        pairs, chunks, JK = nv // 128, len_ // 512, 128
-        bytes_per_launch = {
-            "update": B * (2 * nv * len_ * 4 + pairs * JK * JK * 4),           # read + write every panel, read R
-            "gram": B * (nv * len_ * 4 + pairs * chunks * JK * JK * 4),        # read every panel, write partial Grams
-            "solve": B * (pairs * chunks * JK * JK * 4 + pairs * JK * JK * 4),   # read partial Grams, write R
-        }[dom]
-        avg_s = classes[dom]["ms"] / classes[dom]["launches"] / 1e3
+        pairs, chunks, JK = nv // 128, len_ // 1024, 128
+        x_bytes = B * nv * len_ * 4
+        g_bytes, r_bytes = B * pairs * chunks * JK * JK * 4, B * pairs * JK * JK * 4
+        alg = {"gram": x_bytes + g_bytes, "solve": g_bytes + r_bytes, "update": 2 * x_bytes + r_bytes}
         peak, which = peaks()
-        achieved = bytes_per_launch / avg_s / 1e9
-        traffic = None
+        traffic = {}
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(dom)
-        roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "peak_source": which,
-                    "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_us": avg_s * 1e6,
-                    "class_ms_first_2_sweeps": {k: round(v["ms"], 3) for k, v in classes.items()}}
+            traffic = json.load(open(tpath))
+        per_kernel, t_round = {}, 0.0
+        for k in ("gram", "solve", "update"):
+            us = classes[k]["ms"] / classes[k]["launches"] * 1e3
+            t_round += us
+            per_kernel[k + "_kernel"] = {"avg_launch_us": round(us, 1), "algorithmic_bytes_per_launch": alg[k],
+                                         "achieved_GBps": round(alg[k] / us / 1e3, 1), "frac_of_hbm_peak": round(alg[k] / us / 1e3 / peak, 3),
+                                         "dram_traffic_ncu": traffic.get(k) or traffic.get(k + "_tc")}
+        bytes_round = sum(alg.values())
+        tr = [per_kernel[k + "_kernel"]["dram_traffic_ncu"] for k in ("gram", "solve", "update")]
+        roofline = {"bound": "hbm", "kernel": "jacobi_round = gram_tc_kernel + solve_kernel + update_tc_kernel (one launch each)",
+                    "achieved": bytes_round / t_round / 1e3, "peak": peak, "unit": "GB/s", "frac": bytes_round / t_round / 1e3 / peak,
+                    "traffic": (sum(tr) if all(v is not None for v in tr) else None), "peak_source": which,
+                    "algorithmic_bytes_per_launch": bytes_round, "avg_launch_us": round(t_round, 1),
+                    "note": "solve_kernel is an on-chip (shared-memory / register) Jacobi eigensolver: it moves 18 MB per launch and is "
+                            "bounded by its dependent rotation steps, not by HBM; gram/update are the streaming passes",
+                    "per_kernel": per_kernel,
+                    "class_ms_first_2_sweeps": {k: round(v["ms"], 3) for k, v in classes.items()},
+                    "class_ms_full_factorisation": full_run}
 
     # ---- CPU baseline: the reference's algorithm (oracle port) on this box's host cores, rank 0, N=1 only
     cpu_baseline = None
