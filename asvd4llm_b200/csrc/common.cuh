@@ -80,6 +80,14 @@ __host__ __device__ inline int64_t xt_off(int vec, int col, int nct) {
   return ((int64_t)((vec >> 6) * nct + (col >> 5)) << 11) + ((vec & 63) << 5) + (col & 31);
 }
 
+// Clean-pair tracking (threshold Jacobi across sweeps): per matrix, stamp[blk] = round in which the block was last
+// rotated, clean[I*nb+J] = round in which the pair was last verified orthogonal (or rotated).  A pair whose blocks
+// were not touched since is skipped by all three kernels of a round, so the last sweeps cost almost nothing.
+__device__ __forceinline__ bool pair_is_clean(const int* __restrict__ track, int nb, int b, int I, int J) {
+  const int* t = track + (int64_t)b * (nb + nb * nb);
+  return t[nb + I * nb + J] >= max(t[I], t[J]);
+}
+
 struct SvdPlan {
   int m, n, batch;
   int tall;        // 1: m >= n, vectors are columns of W*s (length m); 0: vectors are rows (length n)
@@ -90,7 +98,7 @@ struct SvdPlan {
   int nb, rounds, pairs, chunks;
   // byte offsets into the workspace
   size_t off_ptrs, off_pairs, off_X, off_Xr, off_Y, off_G, off_R, off_flag, off_maxoff, off_done, off_sigma, off_perm,
-      off_status, off_scale, off_norm;
+      off_status, off_scale, off_norm, off_track;
   size_t bytes;
 };
 

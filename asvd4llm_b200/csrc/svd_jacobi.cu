@@ -106,6 +106,7 @@ SvdPlan make_plan(int m, int n, int batch) {
   p.off_status = take(sizeof(int) * (size_t)batch);
   p.off_scale = take(sizeof(float) * (size_t)batch * n);
   p.off_norm = take(sizeof(float) * (size_t)batch * p.nv_pad);
+  p.off_track = take(sizeof(int) * (size_t)batch * (p.nb + (size_t)p.nb * p.nb));
   p.bytes = off;
   return p;
 }
@@ -151,11 +152,12 @@ __global__ void fill_kernel(float* p, float v, int64_t n) {
 __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, int64_t mat_stride, int ldx,
                                                    const int2* __restrict__ pairs, int len_pad, int chunks,
                                                    int pairs_per_mat, float* __restrict__ Gpart,
-                                                   const int* __restrict__ done) {
+                                                   const int* __restrict__ done, const int* __restrict__ track, int nb) {
   __shared__ __align__(16) float As[2][GK][GLD];
   const int b = blockIdx.z, p = blockIdx.y, c = blockIdx.x;
   if (done[b]) return;
   const int2 pr = pairs[p];
+  if (pair_is_clean(track, nb, b, pr.x, pr.y)) return;
   const float* Xb = X + b * mat_stride;
   const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
   const int row = t >> 1, kq = (t & 1) * 8;
@@ -268,7 +270,8 @@ __device__ __forceinline__ float2 jacobi_scaled(float ghat_pp, float ghat_qq, fl
 __global__ void __launch_bounds__(SOLVE_THREADS, 1)
 solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, float* __restrict__ Rout,
              int* __restrict__ pairflag, unsigned* __restrict__ maxoff_bits, int* __restrict__ status,
-             const int* __restrict__ done, float tol, int transpose_out, int dbg_steps) {
+             const int* __restrict__ done, float tol, int transpose_out, int dbg_steps, const int2* __restrict__ pairs,
+             int* __restrict__ track, int nb, int round_stamp, int precise) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* G = reinterpret_cast<float*>(smem_raw);            // [JK][SLD]; later E = R^T R
   float* Rs = G + JK * SLD;                                 // [JK][SLD]; R in sorted column order (after the sweep)
@@ -284,19 +287,33 @@ solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, flo
   if (done[b]) return;
   const int idx = b * pairs_per_mat + p;
   const int tid = threadIdx.x;
+  const int2 pr = pairs[p];
+  int* trk = track + (int64_t)b * (nb + nb * nb);
+  if (pair_is_clean(track, nb, b, pr.x, pr.y)) {           // untouched since it was last verified: nothing to do
+    if (tid == 0) pairflag[idx] = 0;
+    return;
+  }
   const float* Gp = Gpart + (int64_t)idx * chunks * (JK * JK);
 
-#pragma unroll 4
-  for (int e = tid; e < JK * JK; e += SOLVE_THREADS) {
-    float s = 0.f;
-    int c = 0;
-    for (; c + 4 <= chunks; c += 4) {
-      const float a0 = Gp[(int64_t)c * (JK * JK) + e], a1 = Gp[(int64_t)(c + 1) * (JK * JK) + e];
-      const float a2 = Gp[(int64_t)(c + 2) * (JK * JK) + e], a3 = Gp[(int64_t)(c + 3) * (JK * JK) + e];
-      s += (a0 + a1) + (a2 + a3);
+  {
+    // G = sum of the partial Grams.  16384 elements over 512 threads = 8 float4 per thread and chunk; all loads of
+    // a chunk are issued before the first add so ~32 KB per warp are in flight
+    const float4* Gp4 = reinterpret_cast<const float4*>(Gp);
+    float4 acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < chunks; ++c) {
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = Gp4[(int64_t)c * (JK * JK / 4) + tid + SOLVE_THREADS * i];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { acc[i].x += v[i].x; acc[i].y += v[i].y; acc[i].z += v[i].z; acc[i].w += v[i].w; }
     }
-    for (; c < chunks; ++c) s += Gp[(int64_t)c * (JK * JK) + e];
-    G[(e >> 7) * SLD + (e & (JK - 1))] = s;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int e = (tid + SOLVE_THREADS * i) * 4;
+      *reinterpret_cast<float4*>(&G[(e >> 7) * SLD + (e & (JK - 1))]) = acc[i];
+    }
   }
   if (tid < JK) dsc[tid] = 1.f;
   __syncthreads();
@@ -335,10 +352,16 @@ solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, flo
     if (mx < 1e-2f) atomicAdd(&maxoff_bits[gridDim.y + b], 1u);
   }
   if (mx < tol) {
-    if (tid == 0) pairflag[idx] = 0;
+    if (tid == 0) {
+      pairflag[idx] = 0;
+      if (precise) trk[nb + pr.x * nb + pr.y] = round_stamp;      // verified orthogonal as of this round
+    }
     return;
   }
-  if (tid == 0) pairflag[idx] = 1;
+  if (tid == 0) {
+    pairflag[idx] = 1;
+    trk[pr.x] = round_stamp; trk[pr.y] = round_stamp;             // both blocks change in this round: every pair
+  }                                                               // containing one of them is dirty again
 
   // ---- one odd-even sweep, everything in registers.
   // G threads (256): thread (a, c) keeps the 8x8 patch G[8a.., 8c..] of the FULL symmetric matrix in registers.
@@ -870,6 +893,7 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
   int* status = reinterpret_cast<int*>(ws + p.off_status);
   float* scale = reinterpret_cast<float*>(ws + p.off_scale);
   float* norm = reinterpret_cast<float*>(ws + p.off_norm);
+  int* track = reinterpret_cast<int*>(ws + p.off_track);
   const int64_t xs = (int64_t)p.nv_pad * p.len_pad;
 
   static bool attrs_set = false;
@@ -883,6 +907,14 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
   ASVD_CUDA_CHECK(cudaMemsetAsync(X, 0, sizeof(float) * xs * p.batch, st));
   ASVD_CUDA_CHECK(cudaMemsetAsync(done, 0, sizeof(int) * p.batch, st));
   ASVD_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int) * p.batch, st));
+  {
+    // stamps start at 1, clean marks at 0: every pair is dirty until verified
+    std::vector<int> h_track((size_t)p.batch * (p.nb + (size_t)p.nb * p.nb), 0);
+    for (int b = 0; b < p.batch; ++b)
+      for (int i = 0; i < p.nb; ++i) h_track[(size_t)b * (p.nb + (size_t)p.nb * p.nb) + i] = 1;
+    ASVD_CUDA_CHECK(cudaMemcpyAsync(track, h_track.data(), sizeof(int) * h_track.size(), cudaMemcpyHostToDevice, st));
+    ASVD_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
   {
     dim3 grid((p.n + 31) / 32, (p.m + 31) / 32, p.batch);
     ASVD_LAUNCH(K_PREP, st, (prep_kernel<T><<<grid, 256, 0, st>>>(d_W, scale, ldw, p.m, p.n, p.tall, X, xs, p.len_pad)));
@@ -913,12 +945,13 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
     ASVD_CUDA_CHECK(cudaMemsetAsync(maxoff, 0, sizeof(unsigned) * 2 * p.batch, st));
     for (int r = 0; r < p.rounds; ++r) {
       const int2* pr = d_pairs + (size_t)r * p.pairs;
+      const int round_stamp = 2 + sweep * p.rounds + r;
       if (use_tc) {
-        ASVD_LAUNCH(K_GRAM, st, ASVD_CUDA_CHECK(tc::launch_gram_tc(tmK, pr, p.pairs, p.chunks, GRAM_CHUNK, p.len_pad, p.nv_pad, p.batch, G, done, gram_precise, st)));
+        ASVD_LAUNCH(K_GRAM, st, ASVD_CUDA_CHECK(tc::launch_gram_tc(tmK, pr, p.pairs, p.chunks, GRAM_CHUNK, p.len_pad, p.nv_pad, p.batch, G, done, gram_precise, track, st)));
       } else {
-        ASVD_LAUNCH(K_GRAM, st, (gram_kernel<<<dim3(p.chunks, p.pairs, p.batch), 256, 0, st>>>(X, xs, p.len_pad, pr, p.len_pad, p.chunks, p.pairs, G, done)));
+        ASVD_LAUNCH(K_GRAM, st, (gram_kernel<<<dim3(p.chunks, p.pairs, p.batch), 256, 0, st>>>(X, xs, p.len_pad, pr, p.len_pad, p.chunks, p.pairs, G, done, track, p.nb)));
       }
-      ASVD_LAUNCH(K_SOLVE, st, (solve_kernel<<<dim3(p.pairs, p.batch), SOLVE_THREADS, SOLVE_SMEM, st>>>(G, p.chunks, p.pairs, R, flag, maxoff, status, done, tol, 0, dbg_steps)));
+      ASVD_LAUNCH(K_SOLVE, st, (solve_kernel<<<dim3(p.pairs, p.batch), SOLVE_THREADS, SOLVE_SMEM, st>>>(G, p.chunks, p.pairs, R, flag, maxoff, status, done, tol, 0, dbg_steps, pr, track, p.nb, round_stamp, gram_precise)));
       if (use_tc) {
         ASVD_LAUNCH(K_UPDATE, st, ASVD_CUDA_CHECK(tc::launch_update_tc(tmMN, X, xs, p.len_pad, pr, p.pairs, p.nv_pad, p.len_pad, p.batch, R, flag, done, st)));
       } else {

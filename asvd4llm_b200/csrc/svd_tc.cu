@@ -54,7 +54,7 @@ __device__ __forceinline__ void split_tile(float4* hi, float4* lo, int t) {
 __global__ void __launch_bounds__(GR_THREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__ pairs, int pairs_per_mat, int chunks,
                int chunk_cols, int len_pad, int nv_pad, int n_items, float* __restrict__ Gpart,
-               const int* __restrict__ done, int precise) {
+               const int* __restrict__ done, int precise, const int* __restrict__ track) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + GR_BAR_OFFSET);   // [NH] TMA landed
@@ -87,6 +87,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__
         const int b = item / per_mat, p = (item % per_mat) / chunks, c = item % chunks;
         if (done[b]) continue;
         const int2 pr = pairs[p];
+        if (pair_is_clean(track, nv_pad / JB, b, pr.x, pr.y)) continue;
         const int k0 = c * chunk_cols, k1 = min(len_pad, k0 + chunk_cols);
         for (int k = k0; k < k1; k += 32) {
           mbar_wait(&empty[hs], hph ^ 1);
@@ -109,6 +110,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int b = item / per_mat, c = item % chunks;
         if (done[b]) continue;
+        { const int2 pr = pairs[(item % per_mat) / chunks]; if (pair_is_clean(track, nv_pad / JB, b, pr.x, pr.y)) continue; }
         const int buf = it & 1;
         const uint32_t use = (uint32_t)(it >> 1);
         ++it;
@@ -149,6 +151,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int b = item / per_mat;
       if (done[b]) continue;
+      { const int2 pr = pairs[(item % per_mat) / chunks]; if (pair_is_clean(track, nv_pad / JB, b, pr.x, pr.y)) continue; }
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       ++it;
@@ -177,6 +180,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int b = item / per_mat, c = item % chunks;
       if (done[b]) continue;
+      { const int2 pr = pairs[(item % per_mat) / chunks]; if (pair_is_clean(track, nv_pad / JB, b, pr.x, pr.y)) continue; }
       const int k0 = c * chunk_cols, k1 = min(len_pad, k0 + chunk_cols);
       for (int k = k0; k < k1; k += 32) {
         mbar_wait(&full[hs], hph);
@@ -419,7 +423,7 @@ bool make_x_tmap(CUtensorMap* map, const float* X, int batch, int nv_pad, int le
 }
 
 cudaError_t launch_gram_tc(const CUtensorMap& tmX, const int2* pairs, int pairs_per_mat, int chunks, int chunk_cols,
-                           int len_pad, int nv_pad, int batch, float* Gpart, const int* done, int precise, cudaStream_t st) {
+                           int len_pad, int nv_pad, int batch, float* Gpart, const int* done, int precise, const int* track, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM);
@@ -429,7 +433,7 @@ cudaError_t launch_gram_tc(const CUtensorMap& tmX, const int2* pairs, int pairs_
   const int n_items = batch * pairs_per_mat * chunks;
   const int grid = n_items < sm_count() ? n_items : sm_count();
   gram_tc_kernel<<<grid, GR_THREADS, GR_SMEM, st>>>(tmX, pairs, pairs_per_mat, chunks, chunk_cols, len_pad, nv_pad, n_items,
-                                                    Gpart, done, precise);
+                                                    Gpart, done, precise, track);
   return cudaGetLastError();
 }
 

@@ -61,3 +61,29 @@ def calib_sensitivity_ppl(model, calib_loader, args, use_cache=True, layer_filte
     if layer_filter is None:
         torch.save(table, cache_file)
     return table
+
+
+@torch.no_grad()
+def calib_sensitivity_stable_rank(model, calib_loader, args, use_cache=True):
+    """upstream sensitivity.py:64-110 — sensitivity = -sqrt(|W|_F^2 / sigma_max^2) * ratio^0.1 for nine ratios, values
+    0-d tensors as upstream.  The singular values come from asvd_scaled_svd (no scaling), which also gives
+    |W|_F^2 = sum sigma^2."""
+    from . import _lib
+    model_id = model.config._name_or_path
+    cache_file = (f"cache/{model_id.replace('/', '_')}_sensitivity_stable_rank_{args.scaling_method}_{args.alpha}_"
+                  f"{args.n_calib_samples}_{args.calib_dataset}.pt")
+    if os.path.exists(cache_file) and use_cache:
+        return torch.load(cache_file, map_location="cpu")
+    model.eval()
+    ratios = [0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9]
+    input_ids = torch.cat([b["input_ids"] for b in calib_loader], 0)
+    print(f"input_ids.shape={input_ids.shape}")
+    table = {}
+    for father, name, full_name, raw in enumerate_linears(model):
+        w = raw.weight.data
+        dev = w.device if w.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        sigma = _lib.scaled_svd([w.to(dev)], [None]).sigma(0)
+        sr = ((sigma.double() ** 2).sum() / sigma[0].double() ** 2).sqrt().to(w.dtype).to(w.device)
+        table[full_name] = {ratio: -sr * ratio ** 0.1 for ratio in ratios}
+    torch.save(table, cache_file)
+    return table
