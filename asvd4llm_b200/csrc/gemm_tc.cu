@@ -93,29 +93,33 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value ? 1 : 0, BM, BN);
-      int stage = 0; uint32_t phase = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const uint32_t use = (uint32_t)(it >> 1);
-        mbar_wait(&tempty[buf], (use & 1) ^ 1);
+    // whole warp, uniform control flow; one elected lane issues the MMAs and commits (see elect_one)
+    constexpr uint32_t idesc = make_idesc(sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value ? 1 : 0, BM, BN);
+    const uint64_t adesc0 = make_desc_kmajor_sw128(smem_u32(smem));
+    const uint64_t bdesc0 = make_desc_kmajor_sw128(smem_u32(smem + S::A_BYTES));
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      mbar_wait(&tempty[buf], (use & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+      for (int k = 0; k < num_k; ++k) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
-        for (int k = 0; k < num_k; ++k) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * S::STAGE_BYTES);
-          const uint64_t adesc = make_desc_kmajor_sw128(a_addr);
-          const uint64_t bdesc = make_desc_kmajor_sw128(a_addr + S::A_BYTES);
+        if (elect_one()) {
+          const uint64_t adesc = adesc0 + (uint64_t)(stage * (S::STAGE_BYTES >> 4));
+          const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (S::STAGE_BYTES >> 4));
+          const uint32_t acc0 = k ? 1u : 0u;
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk)          // +32 bytes (>>4 = 2) per K=16 step inside the swizzle atom
-            mma_f16_ss(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) ? 1u : 0u);
+            mma_f16_ss(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, kk ? 1u : acc0);
           tc_commit(&empty[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (k == num_k - 1) tc_commit(&tfull[buf]);
         }
-        tc_commit(&tfull[buf]);
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp >= 4) {

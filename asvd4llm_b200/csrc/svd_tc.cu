@@ -102,47 +102,54 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(2, 128, 128);
-      int hs = 0; uint32_t hph = 0;
-      int ls = 0; uint32_t lph = 0;
-      int it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int b = item / per_mat, c = item % chunks;
-        if (done[b]) continue;
-        { const int2 pr = pairs[(item % per_mat) / chunks]; if (pair_is_clean(track, nv_pad / JB, b, pr.x, pr.y)) continue; }
-        const int buf = it & 1;
-        const uint32_t use = (uint32_t)(it >> 1);
-        ++it;
-        mbar_wait(&tempty[buf], (use & 1) ^ 1);
+    // the whole warp runs the (uniform) loop; one elected lane issues the MMAs and their commits
+    constexpr uint32_t idesc = make_idesc(2, 128, 128);
+    const uint64_t dh0 = make_desc_kmajor_sw128(smem_u32(smem));
+    const uint64_t dl0 = make_desc_kmajor_sw128(smem_u32(smem + GR_LO_OFFSET));
+    int hs = 0; uint32_t hph = 0;
+    int ls = 0; uint32_t lph = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int b = item / per_mat, c = item % chunks;
+      if (done[b]) continue;
+      { const int2 pr = pairs[(item % per_mat) / chunks]; if (pair_is_clean(track, nv_pad / JB, b, pr.x, pr.y)) continue; }
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      ++it;
+      mbar_wait(&tempty[buf], (use & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
+      const int k0 = c * chunk_cols, k1 = min(len_pad, k0 + chunk_cols);
+      for (int k = k0; k < k1; k += 32) {
+        if (precise) mbar_wait(&lo_ready[ls], lph);
+        else mbar_wait(&full[hs], hph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
-        const int k0 = c * chunk_cols, k1 = min(len_pad, k0 + chunk_cols);
-        uint32_t acc = 0;
-        for (int k = k0; k < k1; k += 32) {
-          if (precise) mbar_wait(&lo_ready[ls], lph);
-          else mbar_wait(&full[hs], hph);
-          tc_fence_after();
-          const uint64_t dh = make_desc_kmajor_sw128(smem_u32(smem + hs * GR_HI_BYTES));
-          const uint64_t dl = make_desc_kmajor_sw128(smem_u32(smem + GR_LO_OFFSET + ls * GR_HI_BYTES));
+        if (elect_one()) {
+          const uint64_t dh = dh0 + (uint64_t)(hs * (GR_HI_BYTES >> 4));
+          const uint64_t dl = dl0 + (uint64_t)(ls * (GR_HI_BYTES >> 4));
+          const uint32_t acc0 = (k != k0) ? 1u : 0u;
+          if (precise) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {              // K = 8 tf32 = 32 bytes per step
-            const uint64_t o = (uint64_t)(kk * 2);
-            mma_tf32_ss(d_tmem, dh + o, dh + o, idesc, acc);
-            acc = 1;
-            if (precise) {
+            for (int kk = 0; kk < 4; ++kk) {              // K = 8 tf32 = 32 bytes per step
+              const uint64_t o = (uint64_t)(kk * 2);
+              mma_tf32_ss(d_tmem, dh + o, dh + o, idesc, kk ? 1u : acc0);
               mma_tf32_ss(d_tmem, dl + o, dh + o, idesc, 1u);
               mma_tf32_ss(d_tmem, dh + o, dl + o, idesc, 1u);
             }
+            tc_commit(&lo_empty[ls]);
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t o = (uint64_t)(kk * 2);
+              mma_tf32_ss(d_tmem, dh + o, dh + o, idesc, kk ? 1u : acc0);
+            }
           }
           tc_commit(&empty[hs]);
-          if (++hs == GR_NH) { hs = 0; hph ^= 1; }
-          if (precise) {
-            tc_commit(&lo_empty[ls]);
-            if (++ls == GR_NL) { ls = 0; lph ^= 1; }
-          }
+          if (k + 32 >= k1) tc_commit(&tfull[buf]);
         }
-        tc_commit(&tfull[buf]);
+        __syncwarp();
+        if (++hs == GR_NH) { hs = 0; hph ^= 1; }
+        if (precise) { if (++ls == GR_NL) { ls = 0; lph ^= 1; } }
       }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -272,37 +279,45 @@ update_tc_kernel(const __grid_constant__ CUtensorMap tmX, float* __restrict__ X,
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(2, 128, UP_TN) | (1u << 16);     // B operand MN-major
-      mbar_wait(a_ready, 0);
+    // whole warp, uniform control flow; one elected lane issues (see elect_one)
+    constexpr uint32_t idesc = make_idesc(2, 128, UP_TN) | (1u << 16);     // B operand MN-major
+    const uint64_t bh0 = make_desc_mnmajor_sw128_32b(smem_u32(smem), 16384);
+    const uint64_t bl0 = make_desc_mnmajor_sw128_32b(smem_u32(smem + UP_LO_OFFSET), 16384);
+    mbar_wait(a_ready, 0);
+    tc_fence_after();
+    int stage = 0; uint32_t phase = 0;
+    int ls = 0; uint32_t lph = 0;
+    for (int t = 0; t < ntiles; ++t) {
+      const int buf = t & 1;
+      const uint32_t use = (uint32_t)(t >> 1);
+      mbar_wait(&tempty[buf], (use & 1) ^ 1);
+      mbar_wait(&lo_ready[ls], lph);
       tc_fence_after();
-      int stage = 0; uint32_t phase = 0;
-      int ls = 0; uint32_t lph = 0;
-      for (int t = 0; t < ntiles; ++t) {
-        const int buf = t & 1;
-        const uint32_t use = (uint32_t)(t >> 1);
-        mbar_wait(&tempty[buf], (use & 1) ^ 1);
-        mbar_wait(&lo_ready[ls], lph);
-        tc_fence_after();
+      if (elect_one()) {
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * UP_TN);
-        const uint32_t hi_addr = smem_u32(smem + stage * UP_HI_BYTES);
-        const uint32_t lo_addr = smem_u32(smem + UP_LO_OFFSET + ls * UP_HI_BYTES);
+        const uint64_t bh = bh0 + (uint64_t)(stage * (UP_HI_BYTES >> 4));
+        const uint64_t bl = bl0 + (uint64_t)(ls * (UP_HI_BYTES >> 4));
+        if (!(dbg & 2)) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {                    // K = 8 rows of the tile per step = 1024 bytes
-          const uint64_t bh = make_desc_mnmajor_sw128_32b(hi_addr + k * 1024, 16384);
-          const uint64_t bl = make_desc_mnmajor_sw128_32b(lo_addr + k * 1024, 16384);
-          mma_tf32_ts(d_tmem, tmem_base + UP_TMEM_A_HI + k * 8, bh, idesc, k ? 1u : 0u);
-          if (!(dbg & 2)) {
-            mma_tf32_ts(d_tmem, tmem_base + UP_TMEM_A_LO + k * 8, bh, idesc, 1u);
-            mma_tf32_ts(d_tmem, tmem_base + UP_TMEM_A_HI + k * 8, bl, idesc, 1u);
+          for (int k = 0; k < 16; ++k) {                    // K = 8 rows of the tile per step = 1024 bytes
+            const uint64_t o = (uint64_t)(k * (1024 >> 4));
+            mma_tf32_ts(d_tmem, tmem_base + UP_TMEM_A_HI + k * 8, bh + o, idesc, k ? 1u : 0u);
+            mma_tf32_ts(d_tmem, tmem_base + UP_TMEM_A_LO + k * 8, bh + o, idesc, 1u);
+            mma_tf32_ts(d_tmem, tmem_base + UP_TMEM_A_HI + k * 8, bl + o, idesc, 1u);
           }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            mma_tf32_ts(d_tmem, tmem_base + UP_TMEM_A_HI + k * 8, bh + (uint64_t)(k * (1024 >> 4)), idesc, k ? 1u : 0u);
         }
         tc_commit(&lo_empty[ls]);
         tc_commit(&tfull[buf]);          // the hi slot is handed to the epilogue, which overwrites it with D
-        if (++stage == UP_NH) { stage = 0; phase ^= 1; }
-        if (++ls == UP_NL) { ls = 0; lph ^= 1; }
       }
+      __syncwarp();
+      if (++stage == UP_NH) { stage = 0; phase ^= 1; }
+      if (++ls == UP_NL) { ls = 0; lph ^= 1; }
     }
+    (void)phase;
   } else if (warp >= 4 && warp < 8) {
     const int q = warp - 4;
     const int j = q * 32 + lane;                           // output vector of this thread = TMEM lane

@@ -39,6 +39,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// one lane of a fully converged warp (the same lane every time for the same mask).  Issuing tcgen05.mma / commit
+// under this predicate, with warp-uniform loop control around it, lets the compiler keep descriptors and addresses
+// in uniform registers; a whole `if (lane == 0)` loop instead costs ~40 SASS instructions per MMA (R2UR/ELECT/
+// PLOP3 guards) and makes the issuing thread the bottleneck of a streaming kernel.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // generic-proxy writes to shared memory -> visible to the async proxy (TMA store / UMMA operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
