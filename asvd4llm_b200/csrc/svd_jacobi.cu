@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "svd_tc.h"
+#include "umma.cuh"
 #include <stdlib.h>
 
 namespace asvd {
@@ -267,32 +268,13 @@ __device__ __forceinline__ float2 jacobi_scaled(float ghat_pp, float ghat_qq, fl
     (b) = fmaf((q_).y, _b, _a);        \
   } while (0)
 
-__global__ void __launch_bounds__(SOLVE_THREADS, 1)
-solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, float* __restrict__ Rout,
-             int* __restrict__ pairflag, unsigned* __restrict__ maxoff_bits, int* __restrict__ status,
-             const int* __restrict__ done, float tol, int transpose_out, int dbg_steps, const int2* __restrict__ pairs,
-             int* __restrict__ track, int nb, int round_stamp, int precise) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* G = reinterpret_cast<float*>(smem_raw);            // [JK][SLD]; later E = R^T R
-  float* Rs = G + JK * SLD;                                 // [JK][SLD]; R in sorted column order (after the sweep)
-  float2* cs = reinterpret_cast<float2*>(Rs + JK * SLD);    // [JK/2]
-  float* red = reinterpret_cast<float*>(cs + JK / 2);       // [64]
-  uchar2* tab_even = reinterpret_cast<uchar2*>(red + 64);   // [NB_EVEN] (s, t) of each upper-triangle block
-  uchar2* tab_odd = tab_even + NB_EVEN;                     // [NB_ODD]
-  int* dest = reinterpret_cast<int*>(tab_odd + NB_ODD);     // [JK] output column of each position
-  float* diag = reinterpret_cast<float*>(dest + JK);        // [JK]
-  float* dsc = diag + JK;                                   // [JK] deferred column scales (fast Givens)
-
-  const int b = blockIdx.y, p = blockIdx.x;
-  if (done[b]) return;
-  const int idx = b * pairs_per_mat + p;
-  const int tid = threadIdx.x;
-  const int2 pr = pairs[p];
-  int* trk = track + (int64_t)b * (nb + nb * nb);
-  if (pair_is_clean(track, nb, b, pr.x, pr.y)) {           // untouched since it was last verified: nothing to do
-    if (tid == 0) pairflag[idx] = 0;
-    return;
-  }
+// Common head of the solve kernels: G = sum of the partial Grams into shared memory, convergence measure of the
+// pair at visit time, non-finite check, threshold test and clean-pair bookkeeping.  Returns false when the CTA has
+// nothing to rotate.
+__device__ __forceinline__ bool solve_prologue(const float* __restrict__ Gpart, int chunks, int idx, int b, int2 pr, int tid,
+                                               float* G, float* red, int* __restrict__ pairflag,
+                                               unsigned* __restrict__ maxoff_bits, int* __restrict__ status, float tol,
+                                               int* trk, int nb, int round_stamp, int precise, int nbatch) {
   const float* Gp = Gpart + (int64_t)idx * chunks * (JK * JK);
 
   {
@@ -315,7 +297,6 @@ solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, flo
       *reinterpret_cast<float4*>(&G[(e >> 7) * SLD + (e & (JK - 1))]) = acc[i];
     }
   }
-  if (tid < JK) dsc[tid] = 1.f;
   __syncthreads();
   // convergence measure of this pair at visit time: max |cos| between any two of its 128 vectors
   float mx = 0.f;
@@ -343,25 +324,133 @@ solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, flo
   bad = red[32] > 0.f;
   if (bad) {
     if (tid == 0) { atomicOr(&status[b], 1); pairflag[idx] = 0; }
-    return;
+    return false;
   }
   if (tid == 0) {
     atomicMax(&maxoff_bits[b], __float_as_uint(mx));
     // pairs that are (nearly) orthogonal already: once they appear, the single-pass TF32 Gram would hide them from
     // the threshold test below, so the driver switches to the 3-term split for the next sweep
-    if (mx < 1e-2f) atomicAdd(&maxoff_bits[gridDim.y + b], 1u);
+    if (mx < 1e-2f) atomicAdd(&maxoff_bits[nbatch + b], 1u);
   }
   if (mx < tol) {
     if (tid == 0) {
       pairflag[idx] = 0;
       if (precise) trk[nb + pr.x * nb + pr.y] = round_stamp;      // verified orthogonal as of this round
     }
-    return;
+    return false;
   }
   if (tid == 0) {
     pairflag[idx] = 1;
     trk[pr.x] = round_stamp; trk[pr.y] = round_stamp;             // both blocks change in this round: every pair
   }                                                               // containing one of them is dirty again
+
+  return true;
+}
+
+// Common tail: Rs holds R with its columns in norm-sorted order; one Newton-Schulz step, then the store.
+__device__ __forceinline__ void solve_polish_write(float* G, float* Rs, float* __restrict__ Rout, int idx, int tid,
+                                                   int transpose_out) {
+  // ---- re-orthogonalise, write R
+  // 8x8 register tiles (rows {4ta..} U {64+4ta..}, columns {4tb..} U {64+4tb..}) on the first 256 threads: 64 FMAs
+  // per 4-10 shared-memory loads, so both 128^3 products run at the FMA issue rate
+  float* E = G;
+  const int ta = (tid >> 4) & 15, tb = tid & 15;
+  if (tid < 256) {
+    float e[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) e[i][j] = 0.f;
+#pragma unroll 2
+    for (int l = 0; l < JK; ++l) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&Rs[l * SLD + ta * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&Rs[l * SLD + 64 + ta * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Rs[l * SLD + tb * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Rs[l * SLD + 64 + tb * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[i][j] = fmaf(av[i], bv[j], e[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rr = (i < 4) ? ta * 4 + i : 64 + ta * 4 + (i - 4);
+      *reinterpret_cast<float4*>(&E[rr * SLD + tb * 4]) = make_float4(e[i][0], e[i][1], e[i][2], e[i][3]);
+      *reinterpret_cast<float4*>(&E[rr * SLD + 64 + tb * 4]) = make_float4(e[i][4], e[i][5], e[i][6], e[i][7]);
+    }
+  }
+  __syncthreads();
+  if (tid < 256) {
+    float o[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[i][j] = 0.f;
+    const float* ra = &Rs[(ta * 4) * SLD];
+    const float* rb = &Rs[(64 + ta * 4) * SLD];
+#pragma unroll 2
+    for (int l = 0; l < JK; ++l) {
+      const float4 b0 = *reinterpret_cast<const float4*>(&E[l * SLD + tb * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&E[l * SLD + 64 + tb * 4]);
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const float av[8] = {ra[l], ra[SLD + l], ra[2 * SLD + l], ra[3 * SLD + l], rb[l], rb[SLD + l], rb[2 * SLD + l], rb[3 * SLD + l]};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[i][j] = fmaf(av[i], bv[j], o[i][j]);
+    }
+    float* Ro = Rout + (int64_t)idx * (JK * JK);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rr = (i < 4) ? ta * 4 + i : 64 + ta * 4 + (i - 4);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int cc = hh * 64 + tb * 4;
+        const float4 x = *reinterpret_cast<const float4*>(&Rs[rr * SLD + cc]);
+        const float4 w = make_float4(1.5f * x.x - 0.5f * o[i][4 * hh], 1.5f * x.y - 0.5f * o[i][4 * hh + 1],
+                                     1.5f * x.z - 0.5f * o[i][4 * hh + 2], 1.5f * x.w - 0.5f * o[i][4 * hh + 3]);
+        if (!transpose_out) {
+          *reinterpret_cast<float4*>(&Ro[rr * JK + cc]) = w;
+        } else {
+          Ro[(cc + 0) * JK + rr] = w.x; Ro[(cc + 1) * JK + rr] = w.y; Ro[(cc + 2) * JK + rr] = w.z; Ro[(cc + 3) * JK + rr] = w.w;
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(SOLVE_THREADS, 1)
+solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, float* __restrict__ Rout,
+             int* __restrict__ pairflag, unsigned* __restrict__ maxoff_bits, int* __restrict__ status,
+             const int* __restrict__ done, float tol, int transpose_out, int dbg_steps, const int2* __restrict__ pairs,
+             int* __restrict__ track, int nb, int round_stamp, int precise) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* G = reinterpret_cast<float*>(smem_raw);            // [JK][SLD]; later E = R^T R
+  float* Rs = G + JK * SLD;                                 // [JK][SLD]; R in sorted column order (after the sweep)
+  float2* cs = reinterpret_cast<float2*>(Rs + JK * SLD);    // [JK/2]
+  float* red = reinterpret_cast<float*>(cs + JK / 2);       // [64]
+  uchar2* tab_even = reinterpret_cast<uchar2*>(red + 64);   // [NB_EVEN] (s, t) of each upper-triangle block
+  uchar2* tab_odd = tab_even + NB_EVEN;                     // [NB_ODD]
+  int* dest = reinterpret_cast<int*>(tab_odd + NB_ODD);     // [JK] output column of each position
+  float* diag = reinterpret_cast<float*>(dest + JK);        // [JK]
+  float* dsc = diag + JK;                                   // [JK] deferred column scales (fast Givens)
+
+  const int b = blockIdx.y, p = blockIdx.x;
+  if (done[b]) return;
+  const int idx = b * pairs_per_mat + p;
+  const int tid = threadIdx.x;
+  const int2 pr = pairs[p];
+  int* trk = track + (int64_t)b * (nb + nb * nb);
+  if (pair_is_clean(track, nb, b, pr.x, pr.y)) {           // untouched since it was last verified: nothing to do
+    if (tid == 0) pairflag[idx] = 0;
+    return;
+  }
+  if (!solve_prologue(Gpart, chunks, idx, b, pr, tid, G, red, pairflag, maxoff_bits, status, tol, trk, nb, round_stamp,
+                      precise, gridDim.y))
+    return;
+  if (tid < JK) dsc[tid] = 1.f;      // ordered before its first use by the barriers of the first step
 
   // ---- one odd-even sweep, everything in registers.
   // G threads (256): thread (a, c) keeps the 8x8 patch G[8a.., 8c..] of the FULL symmetric matrix in registers.
@@ -576,76 +665,10 @@ solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, flo
     for (int j = 0; j < JK / 2; ++j) Rs[row * SLD + dest[half * (JK / 2) + j]] = r[j] * dsc[half * (JK / 2) + j];
   }
   __syncthreads();
-  // ---- re-orthogonalise, write R
-  // 8x8 register tiles (rows {4ta..} U {64+4ta..}, columns {4tb..} U {64+4tb..}) on the first 256 threads: 64 FMAs
-  // per 4-10 shared-memory loads, so both 128^3 products run at the FMA issue rate
-  float* E = G;
-  const int ta = (tid >> 4) & 15, tb = tid & 15;
-  if (tid < 256) {
-    float e[8][8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) e[i][j] = 0.f;
-#pragma unroll 2
-    for (int l = 0; l < JK; ++l) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&Rs[l * SLD + ta * 4]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&Rs[l * SLD + 64 + ta * 4]);
-      const float4 b0 = *reinterpret_cast<const float4*>(&Rs[l * SLD + tb * 4]);
-      const float4 b1 = *reinterpret_cast<const float4*>(&Rs[l * SLD + 64 + tb * 4]);
-      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) e[i][j] = fmaf(av[i], bv[j], e[i][j]);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rr = (i < 4) ? ta * 4 + i : 64 + ta * 4 + (i - 4);
-      *reinterpret_cast<float4*>(&E[rr * SLD + tb * 4]) = make_float4(e[i][0], e[i][1], e[i][2], e[i][3]);
-      *reinterpret_cast<float4*>(&E[rr * SLD + 64 + tb * 4]) = make_float4(e[i][4], e[i][5], e[i][6], e[i][7]);
-    }
-  }
-  __syncthreads();
-  if (tid < 256) {
-    float o[8][8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[i][j] = 0.f;
-    const float* ra = &Rs[(ta * 4) * SLD];
-    const float* rb = &Rs[(64 + ta * 4) * SLD];
-#pragma unroll 2
-    for (int l = 0; l < JK; ++l) {
-      const float4 b0 = *reinterpret_cast<const float4*>(&E[l * SLD + tb * 4]);
-      const float4 b1 = *reinterpret_cast<const float4*>(&E[l * SLD + 64 + tb * 4]);
-      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      const float av[8] = {ra[l], ra[SLD + l], ra[2 * SLD + l], ra[3 * SLD + l], rb[l], rb[SLD + l], rb[2 * SLD + l], rb[3 * SLD + l]};
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[i][j] = fmaf(av[i], bv[j], o[i][j]);
-    }
-    float* Ro = Rout + (int64_t)idx * (JK * JK);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rr = (i < 4) ? ta * 4 + i : 64 + ta * 4 + (i - 4);
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int cc = hh * 64 + tb * 4;
-        const float4 x = *reinterpret_cast<const float4*>(&Rs[rr * SLD + cc]);
-        const float4 w = make_float4(1.5f * x.x - 0.5f * o[i][4 * hh], 1.5f * x.y - 0.5f * o[i][4 * hh + 1],
-                                     1.5f * x.z - 0.5f * o[i][4 * hh + 2], 1.5f * x.w - 0.5f * o[i][4 * hh + 3]);
-        if (!transpose_out) {
-          *reinterpret_cast<float4*>(&Ro[rr * JK + cc]) = w;
-        } else {
-          Ro[(cc + 0) * JK + rr] = w.x; Ro[(cc + 1) * JK + rr] = w.y; Ro[(cc + 2) * JK + rr] = w.z; Ro[(cc + 3) * JK + rr] = w.w;
-        }
-      }
-    }
-  }
+  solve_polish_write(G, Rs, Rout, idx, tid, transpose_out);
 }
+
+#include "svd_solve_quad.cuh"
 
 // ------------------------------------------------------------------------------------------------ update
 // panel <- R^T panel, i.e. out[j][c] = sum_i R[i][j] * X[i][c], in place, UPD_TILES column tiles of 128 per CTA.
@@ -899,6 +922,7 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
   static bool attrs_set = false;
   if (!attrs_set) {
     ASVD_CUDA_CHECK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
+    ASVD_CUDA_CHECK(cudaFuncSetAttribute(solve_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVEQ_SMEM));
     ASVD_CUDA_CHECK(cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPDATE_SMEM));
     ASVD_CUDA_CHECK(cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 16384));
     attrs_set = true;
@@ -924,6 +948,10 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
   // tensor-core kernels are tested against); default is the tcgen05 path.
   const char* dbg_env = getenv("ASVD_B200_DBG_STEPS");   // timing experiments only: truncates the inner sweep
   const int dbg_steps = dbg_env ? atoi(dbg_env) : JK / 2;
+  // ASVD_B200_SOLVE=oddeven selects the first-generation inner ordering (kept for A/B runs); default is the quad
+  // round-robin kernel
+  const char* solve_env = getenv("ASVD_B200_SOLVE");
+  const bool solve_quad = !(solve_env && solve_env[0] == 'o') && !dbg_env;
   const char* simt_env = getenv("ASVD_B200_SIMT");
   const bool use_tc = !(simt_env && simt_env[0] == '1');
   CUtensorMap tmK, tmMN;
@@ -951,7 +979,10 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
       } else {
         ASVD_LAUNCH(K_GRAM, st, (gram_kernel<<<dim3(p.chunks, p.pairs, p.batch), 256, 0, st>>>(X, xs, p.len_pad, pr, p.len_pad, p.chunks, p.pairs, G, done, track, p.nb)));
       }
-      ASVD_LAUNCH(K_SOLVE, st, (solve_kernel<<<dim3(p.pairs, p.batch), SOLVE_THREADS, SOLVE_SMEM, st>>>(G, p.chunks, p.pairs, R, flag, maxoff, status, done, tol, 0, dbg_steps, pr, track, p.nb, round_stamp, gram_precise)));
+      if (solve_quad)
+        ASVD_LAUNCH(K_SOLVE, st, (solve_quad_kernel<<<dim3(p.pairs, p.batch), SOLVE_THREADS, SOLVEQ_SMEM, st>>>(G, p.chunks, p.pairs, R, flag, maxoff, status, done, tol, 0, pr, track, p.nb, round_stamp, gram_precise)));
+      else
+        ASVD_LAUNCH(K_SOLVE, st, (solve_kernel<<<dim3(p.pairs, p.batch), SOLVE_THREADS, SOLVE_SMEM, st>>>(G, p.chunks, p.pairs, R, flag, maxoff, status, done, tol, 0, dbg_steps, pr, track, p.nb, round_stamp, gram_precise)));
       if (use_tc) {
         ASVD_LAUNCH(K_UPDATE, st, ASVD_CUDA_CHECK(tc::launch_update_tc(tmMN, X, xs, p.len_pad, pr, p.pairs, p.nv_pad, p.len_pad, p.batch, R, flag, done, st)));
       } else {

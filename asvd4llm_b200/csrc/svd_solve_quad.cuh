@@ -1,0 +1,338 @@
+// solve_quad_kernel: the 128x128 two-sided Jacobi sweep of one block pair in a QUAD ROUND-ROBIN ordering.
+// (included by svd_jacobi.cu after solve_kernel, whose prologue / epilogue it shares.)
+//
+// Why another ordering.  In the odd-even ordering of solve_kernel every step needs the diagonal and the first
+// super-diagonal published through shared memory, two CTA-wide barriers, and on odd steps two boundary exchanges,
+// because the pivot pairs straddle the 8x8 register patches; measured 1.5 us per step, 2/3 of it synchronisation.
+// Here the 128 positions are 32 quads; patch row/column g holds the quads (g, L) = local 0-3 and (g, H) = local 4-7.
+// Pairs are always taken INSIDE an 8-group, so
+//   * the 2x2 pivot blocks lie in the diagonal patches: the 16 diagonal-patch threads compute the rotation
+//     parameters straight from their registers (no publish step, no second barrier);
+//   * a step is: parameters -> one 256-thread barrier -> 128 FMAs per thread, with no data movement at all;
+//   * data moves only once per ROUND (4 steps): the circle method over the 32 quads, (0,L) fixed, the others
+//     advancing one slot along T1..T15,B15..B0, moves whole quads between neighbouring patches through shared memory.
+// Schedule: 3 steps inside the quads ((0,1)(2,3) / (0,2)(1,3) / (0,3)(1,2)), then 31 rounds of 4 steps pairing
+// L_i with H_(i+j)%4, j = 0..3: 127 steps, every pair of positions exactly once.
+// The accumulated rotation R is kept by the other 256 threads as 8x8 patches too (column operations only).  They do
+// not take part in the G barriers: every step's parameters stay in a shared-memory history and the R threads follow
+// behind at their own pace (one single-use mbarrier per step says "published"), filling the issue slots the G threads leave.
+// Rotations are in the scaled (fast Givens) form, one FMA per element and rotation, with the deferred scales folded
+// back every 8 rounds so they stay within 0.707^36.
+
+constexpr int QSTEPS = 127;
+constexpr int QROUNDS = 31;
+constexpr int QFOLDS = 3;                      // after rounds 7, 15, 23
+constexpr size_t SOLVEQ_SMEM = sizeof(float) * (2 * JK * SLD) + sizeof(float2) * QSTEPS * 64 + sizeof(float) * 64 +
+                               sizeof(int) * JK + sizeof(float) * JK * (3 + QFOLDS) + sizeof(uint64_t) * (QSTEPS + 1);
+
+// local positions (p, q) of pair k in a step of the given type: 0-2 inside the quads, 3-6 = L_i with H_(i+type-3)%4
+__host__ __device__ constexpr int qp_p(int type, int k) { return type == 0 ? 2 * k : type <= 2 ? (k < 2 ? k : k + 2) : k; }
+__host__ __device__ constexpr int qp_q(int type, int k) {
+  return type == 0 ? 2 * k + 1
+       : type == 1 ? (k < 2 ? k + 2 : k + 4)
+       : type == 2 ? (k == 0 ? 3 : k == 1 ? 2 : k == 2 ? 7 : 6)
+                   : 4 + ((k + type - 3) & 3);
+}
+
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sqrt_ftz(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rsqrt_ftz(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// Scaled Jacobi rotation of the pivot (p, q): true entries are d_i d_j ghat_ij.  Returns (x, y) = (-beta, alpha) with
+// xhat_p' = xhat_p + x xhat_q, xhat_q' = xhat_q + y xhat_p (old xhat_p), and multiplies both scales by c.
+__device__ __forceinline__ float2 quad_rotation(float gpp, float gqq, float gpq, float& dp, float& dq) {
+  // Everything is written in the stored (scaled) entries: with rho = d_q / d_p,
+  //   tau = (a_qq - a_pp) / (2 a_pq) = (rho ghat_qq - ghat_pp / rho) / (2 ghat_pq),  and the threshold test
+  //   a_pq^2 > eps a_pp a_qq is scale-free.  t = sign(tau) / (|tau| + sqrt(1 + tau^2)) is evaluated with ONE sqrt and
+  //   ONE reciprocal on the dependent chain: t = sign(delta h) |h| / (|delta| + sqrt(delta^2 + h^2)).
+  // Raw approximate MUFU ops: any t gives an exact rotation, and the operands are far from the denormal range (the
+  // scales are folded back every 8 rounds), so the range-scaling code of __fdividef / rsqrtf / sqrtf is dead weight.
+  const float rho = dq * rcp_ftz(dp), rho_inv = dp * rcp_ftz(dq);
+  const float delta = fmaf(rho, gqq, -(gpp * rho_inv)), h = gpq + gpq;
+  float c = 1.f, t = 0.f;
+  if (gpq * gpq > 1e-16f * (gpp * gqq) && gpq != 0.f) {         // |cos| > 1e-8
+    const float s = sqrt_ftz(fmaf(delta, delta, h * h));
+    t = copysignf(fabsf(h) * rcp_ftz(fabsf(delta) + s), delta * h);
+    c = rsqrt_ftz(fmaf(t, t, 1.f));
+  }
+  dp *= c; dq *= c;
+  return make_float2(-t * rho, t * rho_inv);
+}
+
+template <int TYPE>
+__device__ __forceinline__ void quad_rows(float (&g)[8][8], const float2 (&q)[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    constexpr int dummy = 0; (void)dummy;
+    const int p = qp_p(TYPE, k), r = qp_q(TYPE, k);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float a = g[p][j], b = g[r][j];
+      g[p][j] = fmaf(q[k].x, b, a);
+      g[r][j] = fmaf(q[k].y, a, b);
+    }
+  }
+}
+template <int TYPE>
+__device__ __forceinline__ void quad_cols(float (&g)[8][8], const float2 (&q)[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int p = qp_p(TYPE, k), r = qp_q(TYPE, k);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float a = g[i][p], b = g[i][r];
+      g[i][p] = fmaf(q[k].x, b, a);
+      g[i][r] = fmaf(q[k].y, a, b);
+    }
+  }
+}
+
+__device__ __forceinline__ void load_q4(const float2* src, float2 (&q)[4]) {
+  const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 2);
+  q[0] = make_float2(a.x, a.y); q[1] = make_float2(a.z, a.w); q[2] = make_float2(b.x, b.y); q[3] = make_float2(b.z, b.w);
+}
+
+// One step of the G threads.  The LEAD warp (G threads 0-31: the 16 diagonal patches and the 16 patches right of them)
+// computes the four rotations of every group from its registers, publishes them and only ARRIVES at the step's named
+// barrier, so it runs ahead of the other seven warps (which wait on that barrier) by up to a whole round; the barrier
+// ids of a round are distinct and the blocking barriers of the quad move separate their reuse.
+template <int TYPE>
+__device__ __forceinline__ void quad_g_step(float (&g)[8][8], float (&d)[8], bool lead, bool is_diag, float2* cs_step, int pa,
+                                            int pc, int gtid, uint64_t* mb, int step, int bar_id) {
+  if (lead) {
+    if (is_diag) {
+      float2 q[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int p = qp_p(TYPE, k), r = qp_q(TYPE, k);
+        q[k] = quad_rotation(g[p][p], g[r][r], g[p][r], d[p], d[r]);
+      }
+      *reinterpret_cast<float4*>(cs_step + 4 * pa) = make_float4(q[0].x, q[0].y, q[1].x, q[1].y);
+      *reinterpret_cast<float4*>(cs_step + 4 * pa + 2) = make_float4(q[2].x, q[2].y, q[3].x, q[3].y);
+    }
+    __syncwarp();
+    asm volatile("bar.arrive %0, 256;" ::"r"(bar_id) : "memory");
+    if (gtid == 0) tc::mbar_arrive(&mb[step]);             // release: the R threads may consume this step
+  } else {
+    asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+  }
+  float2 qr[4], qc[4];
+  load_q4(cs_step + 4 * pa, qr);
+  load_q4(cs_step + 4 * pc, qc);
+  quad_rows<TYPE>(g, qr);
+  quad_cols<TYPE>(g, qc);
+}
+
+template <int TYPE>
+__device__ __forceinline__ void quad_r_step(float (&r)[8][8], const float2* cs_step, int pc, uint64_t* mb, int step) {
+  tc::mbar_wait(&mb[step], 0);                             // acquire; every barrier of the array is used once
+  float2 qc[4];
+  load_q4(cs_step + 4 * pc, qc);
+  quad_cols<TYPE>(r, qc);
+}
+
+// staging address of chunk `chunk` (float4 index 0..31) of position row `pos`.  Thread lt holds patch
+// (pa, pc) = (lt & 15, (pa + (lt >> 4)) & 15): the 8 lanes of a quarter-warp differ in pa, hence in pc, so both the
+// row-wise accesses (chunk = pc) and the transposed ones (chunk = pa) fall on distinct banks; and the 16 diagonal
+// patches sit in lanes 0-15 of ONE warp, the only one that runs the rotation-parameter code.
+__device__ __forceinline__ float* quad_stage(float* st, int pos, int chunk) { return st + pos * JK + (chunk << 2); }
+// source slot (first position of the quad) whose contents move into quad (g, h) at the end of a round
+__device__ __forceinline__ int quad_src(int g, int h) {
+  if (h == 0) return g <= 1 ? (g == 0 ? 0 : 4) : 8 * (g - 1);
+  return g == 15 ? 8 * 15 : 8 * (g + 1) + 4;
+}
+
+// staging chunk of the column quad that starts at position `pos`
+__device__ __forceinline__ int quad_chunk(int pos) { return ((pos >> 2) & 1) * 16 + (pos >> 3); }
+
+// every thread writes its patch (row 8pa+i, column-quad chunks pc and 16+pc) ...
+__device__ __forceinline__ void quad_stage_write(float* st, const float (&g)[8][8], int pa, int pc) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    *reinterpret_cast<float4*>(quad_stage(st, 8 * pa + i, pc)) = make_float4(g[i][0], g[i][1], g[i][2], g[i][3]);
+    *reinterpret_cast<float4*>(quad_stage(st, 8 * pa + i, 16 + pc)) = make_float4(g[i][4], g[i][5], g[i][6], g[i][7]);
+  }
+}
+// ... and reads the patch its slot holds after the move: rows from the source row quads (rL, rH: first positions; pass
+// 8pa and 8pa+4 when the rows stay), columns from the source column quads
+__device__ __forceinline__ void quad_stage_read(float* st, float (&g)[8][8], int rL, int rH, int cL, int cH) {
+  const int kL = quad_chunk(cL), kH = quad_chunk(cH);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int sp = (i < 4 ? rL : rH) + (i & 3);
+    const float4 lo = *reinterpret_cast<const float4*>(quad_stage(st, sp, kL));
+    const float4 hi = *reinterpret_cast<const float4*>(quad_stage(st, sp, kH));
+    g[i][0] = lo.x; g[i][1] = lo.y; g[i][2] = lo.z; g[i][3] = lo.w;
+    g[i][4] = hi.x; g[i][5] = hi.y; g[i][6] = hi.z; g[i][7] = hi.w;
+  }
+}
+
+__global__ void __launch_bounds__(SOLVE_THREADS, 1)
+solve_quad_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, float* __restrict__ Rout,
+                  int* __restrict__ pairflag, unsigned* __restrict__ maxoff_bits, int* __restrict__ status,
+                  const int* __restrict__ done, float tol, int transpose_out, const int2* __restrict__ pairs,
+                  int* __restrict__ track, int nb, int round_stamp, int precise) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* G = reinterpret_cast<float*>(smem_raw);            // [JK][SLD] summed Gram; staging of the G threads; later E
+  float* Rs = G + JK * SLD;                                 // [JK][SLD] staging of the R threads; then R, sorted columns
+  float2* csh = reinterpret_cast<float2*>(Rs + JK * SLD);   // [QSTEPS][16 groups][4 pairs] rotation history
+  float* red = reinterpret_cast<float*>(csh + QSTEPS * 64); // [64]
+  int* dest = reinterpret_cast<int*>(red + 64);             // [JK] output column of each position
+  float* gd = reinterpret_cast<float*>(dest + JK);          // [JK] final diagonal (true norms)
+  float* dmov = gd + JK;                                    // [JK] scales in transit during a quad move
+  float* dfin = dmov + JK;                                  // [JK] final scales
+  float* dhist = dfin + JK;                                 // [QFOLDS][JK] scales folded into G (and, later, into R)
+  uint64_t* mb = reinterpret_cast<uint64_t*>(dhist + QFOLDS * JK);   // [QSTEPS + 1] one-shot "step published" barriers
+
+  const int b = blockIdx.y, p = blockIdx.x;
+  if (done[b]) return;
+  const int idx = b * pairs_per_mat + p;
+  const int tid = threadIdx.x;
+  const int2 pr = pairs[p];
+  int* trk = track + (int64_t)b * (nb + nb * nb);
+  if (pair_is_clean(track, nb, b, pr.x, pr.y)) {           // untouched since it was last verified: nothing to do
+    if (tid == 0) pairflag[idx] = 0;
+    return;
+  }
+  if (tid < QSTEPS + 1) tc::mbar_init(&mb[tid], 1);         // ordered before their first use by the prologue's barriers
+  if (!solve_prologue(Gpart, chunks, idx, b, pr, tid, G, red, pairflag, maxoff_bits, status, tol, trk, nb, round_stamp,
+                      precise, gridDim.y))
+    return;
+
+  // Warp roles.  A warp's scheduler is warp_id % 4; the lead warp (G warp 0) carries the dependent chain of the
+  // sweep, so it shares scheduler 0 with three R warps (half the work of a G warp, and never ahead of it) while the
+  // other seven G warps and five R warps fill schedulers 1-3.
+  //   warp        0  1  2  3  4  5  6  7  8  9 10 11 12 13 14 15
+  //   role        G0 G1 G2 G3 R0 G4 G5 G6 R1 G7 R2 R3 R4 R5 R6 R7
+  const int wid = tid >> 5;
+  const unsigned g_mask = 0x02EFu;                              // warps 0-3, 5-7, 9
+  const bool is_g = (g_mask >> wid) & 1u;
+  const int ridx = __popc((is_g ? g_mask : ~g_mask) & ((1u << wid) - 1u));   // index among the warps of the same role
+  const int lt = ridx * 32 + (tid & 31);
+  const int pa = lt & 15, pc = (pa + (lt >> 4)) & 15;
+  if (is_g) {
+    // ---------------------------------------------------------------- G threads
+    float g[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 x0 = *reinterpret_cast<const float4*>(&G[(8 * pa + i) * SLD + 8 * pc]);
+      const float4 x1 = *reinterpret_cast<const float4*>(&G[(8 * pa + i) * SLD + 8 * pc + 4]);
+      g[i][0] = x0.x; g[i][1] = x0.y; g[i][2] = x0.z; g[i][3] = x0.w;
+      g[i][4] = x1.x; g[i][5] = x1.y; g[i][6] = x1.z; g[i][7] = x1.w;
+    }
+    float d[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = 1.f;
+    const bool is_diag = (pa == pc);
+    const bool lead = lt < 32;
+    const int rsrcL = quad_src(pa, 0), rsrcH = quad_src(pa, 1);
+    const int csrcL = quad_src(pc, 0), csrcH = quad_src(pc, 1);
+    auto bar_g = [] { asm volatile("bar.sync 2, 256;" ::: "memory"); };
+    bar_g();                                                 // every patch is in registers: G becomes the staging area
+
+    quad_g_step<0>(g, d, lead, is_diag, csh + 0 * 64, pa, pc, lt, mb, 0, 8);
+    quad_g_step<1>(g, d, lead, is_diag, csh + 1 * 64, pa, pc, lt, mb, 1, 9);
+    quad_g_step<2>(g, d, lead, is_diag, csh + 2 * 64, pa, pc, lt, mb, 2, 10);
+#pragma unroll 1
+    for (int r = 0; r < QROUNDS; ++r) {
+      const int s0 = 3 + 4 * r;
+      quad_g_step<3>(g, d, lead, is_diag, csh + (s0 + 0) * 64, pa, pc, lt, mb, s0 + 0, 4);
+      quad_g_step<4>(g, d, lead, is_diag, csh + (s0 + 1) * 64, pa, pc, lt, mb, s0 + 1, 5);
+      quad_g_step<5>(g, d, lead, is_diag, csh + (s0 + 2) * 64, pa, pc, lt, mb, s0 + 2, 6);
+      quad_g_step<6>(g, d, lead, is_diag, csh + (s0 + 3) * 64, pa, pc, lt, mb, s0 + 3, 7);
+      if (r == QROUNDS - 1) break;
+      if ((r & 7) == 7) {
+        // fold the deferred scales back into the stored values
+        float* dh = dhist + (r >> 3) * JK;
+        if (is_diag) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { dh[8 * pa + i] = d[i]; d[i] = 1.f; }
+        }
+        bar_g();
+        float dr[8], dc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { dr[i] = dh[8 * pa + i]; dc[i] = dh[8 * pc + i]; }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[i][j] *= dr[i] * dc[j];
+      }
+      // ---- quad move: one pass through shared memory (rows and columns at once)
+      quad_stage_write(G, g, pa, pc);
+      if (is_diag) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dmov[8 * pa + i] = d[i];
+      }
+      bar_g();
+      quad_stage_read(G, g, rsrcL, rsrcH, csrcL, csrcH);
+      if (is_diag) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = dmov[(i < 4 ? rsrcL : rsrcH) + (i & 3)];
+      }
+      bar_g();               // blocking for the lead warp too: nobody writes the staging area while it is being read
+    }
+    // final diagonal (true norms) and scales, ranks for the norm sort
+    if (is_diag) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { gd[8 * pa + i] = d[i] * d[i] * g[i][i]; dfin[8 * pa + i] = d[i]; }
+    }
+    bar_g();
+    if (lt < JK) {
+      const float dd = gd[lt];
+      int rank = 0;
+      for (int j = 0; j < JK; ++j) {
+        const float e = gd[j];
+        rank += (e > dd) || (e == dd && j < lt);
+      }
+      dest[lt] = rank;
+    }
+    bar_g();
+    if (lt == 0) tc::mbar_arrive(&mb[QSTEPS]);
+  } else {
+    // ---------------------------------------------------------------- R threads
+    float r[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[i][j] = (pa == pc && i == j) ? 1.f : 0.f;
+    const int csrcL = quad_src(pc, 0), csrcH = quad_src(pc, 1);
+    auto bar_r = [] { asm volatile("bar.sync 3, 256;" ::: "memory"); };
+    quad_r_step<0>(r, csh + 0 * 64, pc, mb, 0);
+    quad_r_step<1>(r, csh + 1 * 64, pc, mb, 1);
+    quad_r_step<2>(r, csh + 2 * 64, pc, mb, 2);
+#pragma unroll 1
+    for (int rd = 0; rd < QROUNDS; ++rd) {
+      const int s0 = 3 + 4 * rd;
+      quad_r_step<3>(r, csh + (s0 + 0) * 64, pc, mb, s0 + 0);
+      quad_r_step<4>(r, csh + (s0 + 1) * 64, pc, mb, s0 + 1);
+      quad_r_step<5>(r, csh + (s0 + 2) * 64, pc, mb, s0 + 2);
+      quad_r_step<6>(r, csh + (s0 + 3) * 64, pc, mb, s0 + 3);
+      if (rd == QROUNDS - 1) break;
+      if ((rd & 7) == 7) {
+        // the G threads wrote this fold's scales before publishing the next step
+        tc::mbar_wait(&mb[s0 + 4], 0);
+        const float* dh = dhist + (rd >> 3) * JK;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float dc = dh[8 * pc + j];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) r[i][j] *= dc;
+        }
+      }
+      quad_stage_write(Rs, r, pa, pc);
+      bar_r();
+      quad_stage_read(Rs, r, 8 * pa, 8 * pa + 4, csrcL, csrcH);
+      bar_r();
+    }
+    tc::mbar_wait(&mb[QSTEPS], 0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = dest[8 * pc + j];
+      const float dc = dfin[8 * pc + j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) Rs[(8 * pa + i) * SLD + col] = r[i][j] * dc;
+    }
+  }
+  __syncthreads();
+  solve_polish_write(G, Rs, Rout, idx, tid, transpose_out);
+}
