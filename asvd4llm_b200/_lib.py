@@ -149,6 +149,17 @@ class Factorisation:
         return A, B
 
 
+def suggest_batch(m: int, n: int, device=None, limit_bytes: int = 16 << 30) -> int:
+    """How many same-shape weights to factorise per call: the inner eigen-solve runs one CTA per block pair
+    (128 vectors), one wave of them is the cheapest, and the two streaming passes need one wave's worth of pairs to
+    occupy every SM.  So: as many matrices as fit pairs * batch <= SM count, bounded by workspace memory."""
+    _require_cuda()
+    sms = torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device()).multi_processor_count
+    pairs = (min(m, n) + 127) // 128
+    per = load().asvd_svd_workspace_bytes(int(m), int(n), 1)
+    return int(max(1, min(sms // max(pairs, 1), limit_bytes // max(per, 1), 32)))
+
+
 def scaled_svd(weights: Sequence[torch.Tensor], scales: Optional[Sequence[Optional[torch.Tensor]]] = None,
                tol: float = 0.0, max_sweeps: int = 0, allow_status: Sequence[int] = (ERR_NOT_CONVERGED,)) -> Factorisation:
     """Exact SVD of W_b * diag(scale_b) for a batch of same-shape CUDA weights [m, n]."""

@@ -8,6 +8,7 @@ from collections import defaultdict
 import torch
 import torch.nn as nn
 
+from . import _lib
 from .evaluate_utils import evaluate_perplexity
 from .modules.svd_linear import SVDLinear, from_linear_batch, clear_cache
 from .sensitivity import enumerate_linears
@@ -81,7 +82,7 @@ def search_allocation(model, sensitivity_dict, calib_loader, args):
     return _ratios_after_cut(flat, mid, sensitivity_dict.keys(), default_ratio), default_ratio   # stale mid (:106)
 
 
-def decompose_layers(model, chosen, default_ratio, args, layer_filter=None, batch_limit_bytes=8 << 30):
+def decompose_layers(model, chosen, default_ratio, args, layer_filter=None, batch_limit_bytes=16 << 30):
     """The final pass (binary_search.py:112-128), batching same-shape layers per kernel call.
     Returns the number of layers replaced."""
     by_name = dict(model.named_modules())
@@ -104,8 +105,7 @@ def decompose_layers(model, chosen, default_ratio, args, layer_filter=None, batc
     done = 0
     for (shape, _, _), items in groups.items():
         m, n = shape
-        per = 4 * min(m, n) * (m + n + min(m, n)) + 1
-        step = max(1, min(8, batch_limit_bytes // per))
+        step = _lib.suggest_batch(m, n, limit_bytes=batch_limit_bytes)
         for i in range(0, len(items), step):
             part = items[i:i + step]
             mods = from_linear_batch([raw for _, _, raw in part], [ratio for _, ratio, _ in part], alpha=args.alpha,

@@ -274,7 +274,7 @@ __device__ __forceinline__ float2 jacobi_scaled(float ghat_pp, float ghat_qq, fl
 __device__ __forceinline__ bool solve_prologue(const float* __restrict__ Gpart, int chunks, int idx, int b, int2 pr, int tid,
                                                float* G, float* red, int* __restrict__ pairflag,
                                                unsigned* __restrict__ maxoff_bits, int* __restrict__ status, float tol,
-                                               int* trk, int nb, int round_stamp, int precise, int nbatch) {
+                                               int* trk, int nb, int round_stamp, int precise, int nbatch, int half_gram) {
   const float* Gp = Gpart + (int64_t)idx * chunks * (JK * JK);
 
   {
@@ -298,6 +298,22 @@ __device__ __forceinline__ bool solve_prologue(const float* __restrict__ Gpart, 
     }
   }
   __syncthreads();
+  if (half_gram) {
+    // the tensor-core Gram pass in precise mode delivers T = (0.5 HI + LO) HI^T; the Gram matrix is T + T^T
+    float v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const int e = tid + SOLVE_THREADS * k, r = e >> 7, c = e & (JK - 1);
+      v[k] = G[r * SLD + c] + G[c * SLD + r];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const int e = tid + SOLVE_THREADS * k;
+      G[(e >> 7) * SLD + (e & (JK - 1))] = v[k];
+    }
+    __syncthreads();
+  }
   // convergence measure of this pair at visit time: max |cos| between any two of its 128 vectors
   float mx = 0.f;
   int bad = 0;
@@ -425,7 +441,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1)
 solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, float* __restrict__ Rout,
              int* __restrict__ pairflag, unsigned* __restrict__ maxoff_bits, int* __restrict__ status,
              const int* __restrict__ done, float tol, int transpose_out, int dbg_steps, const int2* __restrict__ pairs,
-             int* __restrict__ track, int nb, int round_stamp, int precise) {
+             int* __restrict__ track, int nb, int round_stamp, int precise, int half_gram) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* G = reinterpret_cast<float*>(smem_raw);            // [JK][SLD]; later E = R^T R
   float* Rs = G + JK * SLD;                                 // [JK][SLD]; R in sorted column order (after the sweep)
@@ -448,7 +464,7 @@ solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, flo
     return;
   }
   if (!solve_prologue(Gpart, chunks, idx, b, pr, tid, G, red, pairflag, maxoff_bits, status, tol, trk, nb, round_stamp,
-                      precise, gridDim.y))
+                      precise, gridDim.y, half_gram))
     return;
   if (tid < JK) dsc[tid] = 1.f;      // ordered before its first use by the barriers of the first step
 
@@ -974,15 +990,16 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
     for (int r = 0; r < p.rounds; ++r) {
       const int2* pr = d_pairs + (size_t)r * p.pairs;
       const int round_stamp = 2 + sweep * p.rounds + r;
+      const int half_gram = (use_tc && gram_precise) ? 1 : 0;   // gram_tc_kernel's precise mode stores T, G = T + T^T
       if (use_tc) {
         ASVD_LAUNCH(K_GRAM, st, ASVD_CUDA_CHECK(tc::launch_gram_tc(tmK, pr, p.pairs, p.chunks, GRAM_CHUNK, p.len_pad, p.nv_pad, p.batch, G, done, gram_precise, track, st)));
       } else {
         ASVD_LAUNCH(K_GRAM, st, (gram_kernel<<<dim3(p.chunks, p.pairs, p.batch), 256, 0, st>>>(X, xs, p.len_pad, pr, p.len_pad, p.chunks, p.pairs, G, done, track, p.nb)));
       }
       if (solve_quad)
-        ASVD_LAUNCH(K_SOLVE, st, (solve_quad_kernel<<<dim3(p.pairs, p.batch), SOLVE_THREADS, SOLVEQ_SMEM, st>>>(G, p.chunks, p.pairs, R, flag, maxoff, status, done, tol, 0, pr, track, p.nb, round_stamp, gram_precise)));
+        ASVD_LAUNCH(K_SOLVE, st, (solve_quad_kernel<<<dim3(p.pairs, p.batch), SOLVE_THREADS, SOLVEQ_SMEM, st>>>(G, p.chunks, p.pairs, R, flag, maxoff, status, done, tol, 0, pr, track, p.nb, round_stamp, gram_precise, half_gram)));
       else
-        ASVD_LAUNCH(K_SOLVE, st, (solve_kernel<<<dim3(p.pairs, p.batch), SOLVE_THREADS, SOLVE_SMEM, st>>>(G, p.chunks, p.pairs, R, flag, maxoff, status, done, tol, 0, dbg_steps, pr, track, p.nb, round_stamp, gram_precise)));
+        ASVD_LAUNCH(K_SOLVE, st, (solve_kernel<<<dim3(p.pairs, p.batch), SOLVE_THREADS, SOLVE_SMEM, st>>>(G, p.chunks, p.pairs, R, flag, maxoff, status, done, tol, 0, dbg_steps, pr, track, p.nb, round_stamp, gram_precise, half_gram)));
       if (use_tc) {
         ASVD_LAUNCH(K_UPDATE, st, ASVD_CUDA_CHECK(tc::launch_update_tc(tmMN, X, xs, p.len_pad, pr, p.pairs, p.nv_pad, p.len_pad, p.batch, R, flag, done, st)));
       } else {

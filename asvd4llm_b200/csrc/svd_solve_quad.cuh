@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1)
 solve_quad_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, float* __restrict__ Rout,
                   int* __restrict__ pairflag, unsigned* __restrict__ maxoff_bits, int* __restrict__ status,
                   const int* __restrict__ done, float tol, int transpose_out, const int2* __restrict__ pairs,
-                  int* __restrict__ track, int nb, int round_stamp, int precise) {
+                  int* __restrict__ track, int nb, int round_stamp, int precise, int half_gram) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* G = reinterpret_cast<float*>(smem_raw);            // [JK][SLD] summed Gram; staging of the G threads; later E
   float* Rs = G + JK * SLD;                                 // [JK][SLD] staging of the R threads; then R, sorted columns
@@ -196,7 +196,7 @@ solve_quad_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat
   }
   if (tid < QSTEPS + 1) tc::mbar_init(&mb[tid], 1);         // ordered before their first use by the prologue's barriers
   if (!solve_prologue(Gpart, chunks, idx, b, pr, tid, G, red, pairflag, maxoff_bits, status, tol, trk, nb, round_stamp,
-                      precise, gridDim.y))
+                      precise, gridDim.y, half_gram))
     return;
 
   // Warp roles.  A warp's scheduler is warp_id % 4; the lead warp (G warp 0) carries the dependent chain of the

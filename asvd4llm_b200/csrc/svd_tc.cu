@@ -7,11 +7,16 @@
 //
 // gram_tc_kernel: G_c = P_c P_c^T for the 128-vector panel of a block pair over a chunk of columns.  Both MMA
 // operands are the SAME K-major tile (vectors are rows of X, the contraction runs along the contiguous dimension).
-//   warp 0  TMA producer (two 64-row boxes per stage: block I rows, block J rows), 128-byte swizzle, 4 stages
-//   warp 1  MMA issuer: 4 K-steps x 3 split terms of tcgen05.mma M=128 N=128 K=8 per stage
-//   warp 2  TMEM allocator (2 accumulators x 128 columns)
+//   warp 0  TMA producer (two 64-row boxes per stage: block I rows, block J rows), 128-byte swizzle
+//   warp 1  MMA issuer (whole warp, one elected lane): 4 K-steps of tcgen05.mma M=128 N=128 K=8 per stage
+//   warp 2  TMEM allocator
 //   warps 4-7  epilogue: tcgen05.ld -> global partial Gram
-//   warps 8-11 split: hi/lo rewrite of the landed tile, fence.proxy.async, arrive
+//   warps 8-11 split (precise mode): thread t owns row t of the landed tile; hi = rna_tf32(x) goes back in place, the
+//              A operand (0.5 hi | lo) goes to TENSOR MEMORY (tcgen05.st)
+// Precise mode computes only T = (0.5 HI + LO) HI^T -- two MMAs per K-step, A from tensor memory, B = the hi tile
+// in shared memory -- and the solve kernel forms G = T + T^T = HI HI^T + LO HI^T + HI LO^T.  Against three
+// shared-memory MMAs per K-step this halves the shared-memory traffic per landed byte (the old bound of this
+// kernel: 10 bytes moved per byte landed) and needs no lo tile in shared memory at all.
 #include <type_traits>
 #include <stdlib.h>
 #include "common.cuh"
@@ -20,11 +25,11 @@
 namespace asvd {
 namespace tc {
 
-constexpr int GR_NH = 8;                        // landing ring (TMA -> hi tiles): 8 x 16 KB in flight per SM
-constexpr int GR_NL = 3;                         // lo ring (split warps -> MMA)
+constexpr int GR_NH = 10;                        // landing ring (TMA -> hi tiles): 10 x 16 KB in flight per SM
+constexpr int GR_NA = 4;                         // A-operand ring in tensor memory: 64 columns (0.5 hi | lo) per stage
 constexpr int GR_HI_BYTES = 128 * 128;           // 128 rows x 32 floats
-constexpr int GR_LO_OFFSET = GR_NH * GR_HI_BYTES;
-constexpr int GR_BAR_OFFSET = GR_LO_OFFSET + GR_NL * GR_HI_BYTES;
+constexpr int GR_BAR_OFFSET = GR_NH * GR_HI_BYTES;
+constexpr uint32_t GR_TMEM_A = 256;              // accumulators at columns 0 and 128, A ring from column 256
 constexpr int GR_SMEM = GR_BAR_OFFSET + 512 + 1024;
 constexpr int GR_THREADS = 384;
 
@@ -59,9 +64,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + GR_BAR_OFFSET);   // [NH] TMA landed
   uint64_t* empty = full + GR_NH;                                        // [NH] MMAs reading the hi tile retired
-  uint64_t* lo_ready = empty + GR_NH;                                    // [NL] split done (hi rewritten, lo written)
-  uint64_t* lo_empty = lo_ready + GR_NL;                                 // [NL]
-  uint64_t* tfull = lo_empty + GR_NL;
+  uint64_t* a_ready = empty + GR_NH;                                     // [NA] split done (hi rewritten, A in TMEM)
+  uint64_t* a_empty = a_ready + GR_NA;                                   // [NA] MMAs reading the A stage retired
+  uint64_t* tfull = a_empty + GR_NA;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -69,11 +74,11 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tmX);
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < GR_NH; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < GR_NL; ++i) { mbar_init(&lo_ready[i], 4); mbar_init(&lo_empty[i], 1); }
+    for (int i = 0; i < GR_NA; ++i) { mbar_init(&a_ready[i], 4); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_ptr, 256);
+  if (warp == 2) tmem_alloc(tmem_ptr, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -105,9 +110,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__
     // the whole warp runs the (uniform) loop; one elected lane issues the MMAs and their commits
     constexpr uint32_t idesc = make_idesc(2, 128, 128);
     const uint64_t dh0 = make_desc_kmajor_sw128(smem_u32(smem));
-    const uint64_t dl0 = make_desc_kmajor_sw128(smem_u32(smem + GR_LO_OFFSET));
     int hs = 0; uint32_t hph = 0;
-    int ls = 0; uint32_t lph = 0;
+    int as = 0; uint32_t aph = 0;
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int b = item / per_mat, c = item % chunks;
@@ -121,22 +125,21 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
       const int k0 = c * chunk_cols, k1 = min(len_pad, k0 + chunk_cols);
       for (int k = k0; k < k1; k += 32) {
-        if (precise) mbar_wait(&lo_ready[ls], lph);
+        if (precise) mbar_wait(&a_ready[as], aph);
         else mbar_wait(&full[hs], hph);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t dh = dh0 + (uint64_t)(hs * (GR_HI_BYTES >> 4));
-          const uint64_t dl = dl0 + (uint64_t)(ls * (GR_HI_BYTES >> 4));
           const uint32_t acc0 = (k != k0) ? 1u : 0u;
           if (precise) {
+            const uint32_t a_tmem = tmem_base + GR_TMEM_A + (uint32_t)(as * 64);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {              // K = 8 tf32 = 32 bytes per step
+            for (int kk = 0; kk < 4; ++kk) {              // K = 8 tf32 = 32 bytes of B, 8 columns of A per step
               const uint64_t o = (uint64_t)(kk * 2);
-              mma_tf32_ss(d_tmem, dh + o, dh + o, idesc, kk ? 1u : acc0);
-              mma_tf32_ss(d_tmem, dl + o, dh + o, idesc, 1u);
-              mma_tf32_ss(d_tmem, dh + o, dl + o, idesc, 1u);
+              mma_tf32_ts(d_tmem, a_tmem + kk * 8, dh + o, idesc, kk ? 1u : acc0);          // 0.5 hi * hi^T
+              mma_tf32_ts(d_tmem, a_tmem + 32 + kk * 8, dh + o, idesc, 1u);                 // lo * hi^T
             }
-            tc_commit(&lo_empty[ls]);
+            tc_commit(&a_empty[as]);
           } else {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
@@ -149,7 +152,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__
         }
         __syncwarp();
         if (++hs == GR_NH) { hs = 0; hph ^= 1; }
-        if (precise) { if (++ls == GR_NL) { ls = 0; lph ^= 1; } }
+        if (precise) { if (++as == GR_NA) { as = 0; aph ^= 1; } }
       }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -181,9 +184,10 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__
       if (lane == 0) mbar_arrive(&tempty[buf]);
     }
   } else if (warp >= 8 && precise) {
-    const int t = threadIdx.x - 256;
+    const int t = threadIdx.x - 256;                         // row of the tile = TMEM lane; warp 8+q owns lanes 32q..
+    const int q = warp - 8;
     int hs = 0; uint32_t hph = 0;
-    int ls = 0; uint32_t lph = 0;
+    int as = 0; uint32_t aph = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int b = item / per_mat, c = item % chunks;
       if (done[b]) continue;
@@ -191,20 +195,42 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__
       const int k0 = c * chunk_cols, k1 = min(len_pad, k0 + chunk_cols);
       for (int k = k0; k < k1; k += 32) {
         mbar_wait(&full[hs], hph);
-        mbar_wait(&lo_empty[ls], lph ^ 1);
-        split_tile(reinterpret_cast<float4*>(smem + hs * GR_HI_BYTES),
-                   reinterpret_cast<float4*>(smem + GR_LO_OFFSET + ls * GR_HI_BYTES), t);
+        // row t of the 128-byte-swizzled tile: 16-byte chunk j lives at chunk j ^ (t & 7)
+        unsigned char* row = smem + hs * GR_HI_BYTES + t * 128;
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(row + ((j ^ (t & 7)) << 4));
+        uint32_t hh[32], lo[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float x[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+          float h[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            h[e] = rna_tf32(x[e]);
+            hh[4 * j + e] = __float_as_uint(0.5f * h[e]);
+            lo[4 * j + e] = __float_as_uint(x[e] - h[e]);
+          }
+          *reinterpret_cast<float4*>(row + ((j ^ (t & 7)) << 4)) = make_float4(h[0], h[1], h[2], h[3]);
+        }
+        mbar_wait(&a_empty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t a_tmem = tmem_base + ((uint32_t)(q * 32) << 16) + GR_TMEM_A + (uint32_t)(as * 64);
+        tmem_st_32x32b_x32(a_tmem, hh);
+        tmem_st_32x32b_x32(a_tmem + 32, lo);
+        tmem_st_wait();
         fence_proxy_async_smem();
+        tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&lo_ready[ls]);
+        if (lane == 0) mbar_arrive(&a_ready[as]);
         if (++hs == GR_NH) { hs = 0; hph ^= 1; }
-        if (++ls == GR_NL) { ls = 0; lph ^= 1; }
+        if (++as == GR_NA) { as = 0; aph ^= 1; }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 256);
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------ update

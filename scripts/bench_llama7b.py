@@ -33,7 +33,6 @@ def main():
     for i, (name, m, n) in enumerate(L):
         if name in mine:
             shapes.setdefault((m, n), []).append((i, name))
-    batch_cap = {(4096, 4096): 4, (11008, 4096): 2, (4096, 11008): 2}
     _lib.load()
     # warm-up (library load, attribute set-up) on a small problem
     _lib.scaled_svd([torch.randn(256, 256, device=dev).half()], [None])
@@ -42,7 +41,7 @@ def main():
     t0 = time.perf_counter()
     per_shape, checks, done, sweeps_seen = {}, [], 0, {}
     for (m, n), items in shapes.items():
-        cap = batch_cap.get((m, n), 1)
+        cap = _lib.suggest_batch(m, n, dev)
         ts = time.perf_counter()
         r = _lib.rank_for_ratio(m, n, 0.9, 1)
         for j in range(0, len(items), cap):
