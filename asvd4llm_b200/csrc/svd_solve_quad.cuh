@@ -39,8 +39,8 @@ __device__ __forceinline__ float sqrt_ftz(float x) { float y; asm("sqrt.approx.f
 __device__ __forceinline__ float rsqrt_ftz(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // Scaled Jacobi rotation of the pivot (p, q): true entries are d_i d_j ghat_ij.  Returns (x, y) = (-beta, alpha) with
-// xhat_p' = xhat_p + x xhat_q, xhat_q' = xhat_q + y xhat_p (old xhat_p), and multiplies both scales by c.
-__device__ __forceinline__ float2 quad_rotation(float gpp, float gqq, float gpq, float& dp, float& dq) {
+// xhat_p' = xhat_p + x xhat_q, xhat_q' = xhat_q + y xhat_p (old xhat_p), and z = c, the factor both scales take.
+__device__ __forceinline__ float3 quad_rotation(float gpp, float gqq, float gpq, float dp, float dq) {
   // Everything is written in the stored (scaled) entries: with rho = d_q / d_p,
   //   tau = (a_qq - a_pp) / (2 a_pq) = (rho ghat_qq - ghat_pp / rho) / (2 ghat_pq),  and the threshold test
   //   a_pq^2 > eps a_pp a_qq is scale-free.  t = sign(tau) / (|tau| + sqrt(1 + tau^2)) is evaluated with ONE sqrt and
@@ -55,8 +55,7 @@ __device__ __forceinline__ float2 quad_rotation(float gpp, float gqq, float gpq,
     t = copysignf(fabsf(h) * rcp_ftz(fabsf(delta) + s), delta * h);
     c = rsqrt_ftz(fmaf(t, t, 1.f));
   }
-  dp *= c; dq *= c;
-  return make_float2(-t * rho, t * rho_inv);
+  return make_float3(-t * rho, t * rho_inv, c);
 }
 
 template <int TYPE>
@@ -100,15 +99,41 @@ template <int TYPE>
 __device__ __forceinline__ void quad_g_step(float (&g)[8][8], float (&d)[8], bool lead, bool is_diag, float2* cs_step, int pa,
                                             int pc, int gtid, uint64_t* mb, int step, int bar_id) {
   if (lead) {
-    if (is_diag) {
-      float2 q[4];
+    // The parameter arithmetic is the dependent chain of the whole sweep (~35 instructions per pivot at ~4 cycles
+    // each for a single warp), so it is spread over all 32 lanes: diagonal lane L keeps pivots 0 and 1 and hands
+    // pivots 2 and 3 to lane L + 16 (whose own patch needs no parameters), 10 shuffles out and 6 back.
+    const int lane = gtid & 31;
+    const bool upper = lane >= 16;
+    float in[2][5];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int p = qp_p(TYPE, k), r = qp_q(TYPE, k);
-        q[k] = quad_rotation(g[p][p], g[r][r], g[p][r], d[p], d[r]);
+    for (int kk = 0; kk < 2; ++kk) {
+      const int pl = qp_p(TYPE, kk), rl = qp_q(TYPE, kk), ph = qp_p(TYPE, kk + 2), rh = qp_q(TYPE, kk + 2);
+      const float mine[5] = {g[pl][pl], g[rl][rl], g[pl][rl], d[pl], d[rl]};
+      const float send[5] = {g[ph][ph], g[rh][rh], g[ph][rh], d[ph], d[rh]};
+#pragma unroll
+      for (int v = 0; v < 5; ++v) {
+        const float got = __shfl_sync(0xffffffffu, send[v], lane & 15);
+        in[kk][v] = upper ? got : mine[v];
       }
-      *reinterpret_cast<float4*>(cs_step + 4 * pa) = make_float4(q[0].x, q[0].y, q[1].x, q[1].y);
-      *reinterpret_cast<float4*>(cs_step + 4 * pa + 2) = make_float4(q[2].x, q[2].y, q[3].x, q[3].y);
+    }
+    float3 o[2];
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) o[kk] = quad_rotation(in[kk][0], in[kk][1], in[kk][2], in[kk][3], in[kk][4]);
+    float3 back[2];
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      back[kk].x = __shfl_sync(0xffffffffu, o[kk].x, (lane & 15) + 16);
+      back[kk].y = __shfl_sync(0xffffffffu, o[kk].y, (lane & 15) + 16);
+      back[kk].z = __shfl_sync(0xffffffffu, o[kk].z, (lane & 15) + 16);
+    }
+    if (is_diag) {
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        d[qp_p(TYPE, kk)] *= o[kk].z; d[qp_q(TYPE, kk)] *= o[kk].z;
+        d[qp_p(TYPE, kk + 2)] *= back[kk].z; d[qp_q(TYPE, kk + 2)] *= back[kk].z;
+      }
+      *reinterpret_cast<float4*>(cs_step + 4 * pa) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+      *reinterpret_cast<float4*>(cs_step + 4 * pa + 2) = make_float4(back[0].x, back[0].y, back[1].x, back[1].y);
     }
     __syncwarp();
     asm volatile("bar.arrive %0, 256;" ::"r"(bar_id) : "memory");
