@@ -1,14 +1,18 @@
 // tcgen05 GEMM for the low-rank forward (a7): C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]), 16-bit operands (both
 // K-major, as activations [tokens, features] and nn.Linear weights [out, in] are), fp32 accumulation in TMEM.
 //
-// Persistent, warp-specialised, one CTA per SM:
-//   warp 0     TMA producer : 128 x 64 tile of A and BN x 64 tile of B per stage (128-byte swizzle), 3 stages
+// Persistent, warp-specialised, one CTA per SM, launched as CLUSTERS OF TWO CTAs that work on vertically adjacent
+// output tiles (same columns): each CTA fetches half of the B tile and TMA-multicasts it to both, so the weight
+// operand -- re-read from L2 once per 128 output rows -- crosses the L2 -> SM fabric once per 256 rows.  (Measured before
+// this: x B^T at r = 256 moved 1.07 GB of weights through L2 next to 0.54 GB of activations and ran at the L2 cap.)
+//   warp 0     TMA producer : 128 x 64 tile of A and half of the BN x 64 tile of B per stage (128-byte swizzle), 3 stages;
+//                             a stage is refilled when the MMAs of BOTH CTAs have retired it
 //   warp 1     MMA issuer   : one elected thread issues 4 x tcgen05.mma (M=128, N=BN, K=16) per stage into one of
 //                             two TMEM accumulators; tcgen05.commit releases the stage / publishes the accumulator
 //   warp 2     TMEM allocator (2 x BN columns)
 //   warps 4-11 epilogue     : tcgen05.ld (32 lanes x 32 columns per warp and step) -> + bias -> 16-bit -> swizzled
-//                             staging tile in shared memory -> TMA store (full 128-byte lines), overlapped with the
-//                             next tile's MMAs through the second accumulator
+//                             16 KB staging buffer per 128-column half, 64 columns at a time -> TMA store (full 128-byte
+//                             lines), overlapped with the next tile's MMAs through the second accumulator
 // SVDLinear.forward = two launches: t = x B^T, y = t A^T + b (the [tokens, r] intermediate stays L2-resident for
 // the sizes of BASELINE config 4: 64 Ki x 256 x 2 B = 32 MiB per 128 MiB L2).
 #include "common.cuh"
@@ -20,16 +24,20 @@ namespace tc {
 
 constexpr int BM = 128;
 constexpr int BK = 64;            // 16-bit elements per stage row = 128 bytes = one swizzle atom
-constexpr int STAGES = 3;
 constexpr int GEMM_THREADS = 384;      // warps 0-3: producer / MMA / TMEM alloc / spare; warps 4-11: epilogue
-constexpr int STAGING_HALF = BM * 128 * 2;   // one 128-column half of the output tile: 2 groups of [128 rows x 128 B]
+constexpr int STAGING_HALF = BM * 128;       // 64 output columns of one 128-column half: [128 rows x 128 B], used twice per tile
 
-template <int BN> struct GemmSmem {
+// NBUF = staging buffers per 128-column half.  Long-K products (x B^T) are bound by activation bytes in flight: 4 stages
+// (3 in flight = 48 KB per SM; scripts/probes/stream_probe.cu: 32 KB caps at 5.2 TB/s) and one staging buffer.  Short-K
+// products (t A^T) are bound by output stores in flight: 3 stages and two staging buffers per half, so two 16 KB TMA
+// stores per half are outstanding.
+template <int BN, int NBUF> struct GemmSmem {
+  static constexpr int STAGES = NBUF == 1 ? 4 : 3;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFFSET = STAGING_OFFSET + (BN / 128) * STAGING_HALF;
+  static constexpr int BAR_OFFSET = STAGING_OFFSET + (BN / 128) * NBUF * STAGING_HALF;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + tmem pointer + alignment slack
 };
 
@@ -43,11 +51,12 @@ template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, fl
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <typename T, int BN>
+template <typename T, int BN, int NBUF>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const T* __restrict__ bias, int M, int N, int K) {
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, NBUF>;
+  constexpr int STAGES = S::STAGES;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
@@ -58,8 +67,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
+  const int num_tiles = ((num_m + 1) / 2) * num_n;          // pairs of vertically adjacent tiles, one pair per cluster
   const int num_k = (K + BK - 1) / BK;
+  const int crank = (int)cluster_ctarank();
+  const int cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -67,27 +78,29 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 2); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * (BN / 128)); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr, 2 * BN);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();              // the peer's barriers exist before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m0 = (t / num_n) * BM, n0 = (t % num_n) * BN;
+      for (int t = cid; t < num_tiles; t += nclusters) {
+        const int m0 = ((t / num_n) * 2 + crank) * BM, n0 = (t % num_n) * BN;
         for (int k = 0; k < num_k; ++k) {
           mbar_wait(&empty[stage], phase ^ 1);
           unsigned char* a = smem + stage * S::STAGE_BYTES;
-          mbar_arrive_expect_tx(&full[stage], S::STAGE_BYTES);
+          mbar_arrive_expect_tx(&full[stage], S::STAGE_BYTES);     // own A tile + both halves of the B tile
           tma_load_2d(a, &tmA, &full[stage], k * BK, m0);
-          tma_load_2d(a + S::A_BYTES, &tmB, &full[stage], k * BK, n0);
+          tma_load_2d_multicast(a + S::A_BYTES + crank * (S::B_BYTES / 2), &tmB, &full[stage], k * BK, n0 + crank * (BN / 2),
+                                (uint16_t)3);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -99,7 +112,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint64_t bdesc0 = make_desc_kmajor_sw128(smem_u32(smem + S::A_BYTES));
     int stage = 0; uint32_t phase = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (int t = cid; t < num_tiles; t += nclusters, ++it) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       mbar_wait(&tempty[buf], (use & 1) ^ 1);
@@ -115,7 +128,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk)          // +32 bytes (>>4 = 2) per K=16 step inside the swizzle atom
             mma_f16_ss(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, kk ? 1u : acc0);
-          tc_commit(&empty[stage]);
+          tc_commit_multicast(&empty[stage], (uint16_t)3);     // this CTA is done with the stage: tell both producers
           if (k == num_k - 1) tc_commit(&tfull[buf]);
         }
         __syncwarp();
@@ -128,71 +141,92 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = (warp - 4) & 3, h = (warp - 4) >> 2;
     const bool active = h < BN / 128;
     const int r = q * 32 + lane;                                  // row of the tile = TMEM lane
-    unsigned char* stg = smem + S::STAGING_OFFSET + h * STAGING_HALF;
-    int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    unsigned char* stg_base = smem + S::STAGING_OFFSET + h * NBUF * STAGING_HALF;
+    int it = 0, nstore = 0;
+    for (int t = cid; t < num_tiles; t += nclusters, ++it) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
-      const int m0 = (t / num_n) * BM, n0 = (t % num_n) * BN;
+      const int m0 = ((t / num_n) * 2 + crank) * BM, n0 = (t % num_n) * BN;
       if (!active) continue;
       mbar_wait(&tfull[buf], use & 1);
       tc_fence_after();
-      // the previous tile's store must have finished reading this half's staging buffer
-      if (q == 0 && lane == 0) tma_store_wait_read<0>();
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + h) : "memory");
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + h * 128 + c * 32), v);
-        tmem_ld_wait();
-        const int col0 = n0 + h * 128 + c * 32;
-        float f[32];
+      for (int sub = 0; sub < 2; ++sub) {                          // 64 columns at a time through a 16 KB staging buffer
+        // the store that last used this staging buffer must have finished reading it
+        unsigned char* stg = stg_base + (nstore % NBUF) * STAGING_HALF;
+        ++nstore;
+        if (q == 0 && lane == 0) tma_store_wait_read<NBUF - 1>();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + h) : "memory");
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (bias) {
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = 2 * sub + cc;
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + h * 128 + c * 32), v);
+          tmem_ld_wait();
+          const int col0 = n0 + h * 128 + c * 32;
+          float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) if (col0 + j < N) f[j] += to_f32<T>(bias[col0 + j]);
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (col0 + j < N) f[j] += to_f32<T>(bias[col0 + j]);
+          }
+          // 32 columns = 64 bytes = chunks 4*cc .. +3 of the 128-byte row
+          unsigned char* rowp = stg + r * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int chunk = (cc * 4 + j) ^ (r & 7);
+            *reinterpret_cast<uint4*>(rowp + chunk * 16) =
+                make_uint4(pack2<T>(f[8 * j], f[8 * j + 1]), pack2<T>(f[8 * j + 2], f[8 * j + 3]),
+                           pack2<T>(f[8 * j + 4], f[8 * j + 5]), pack2<T>(f[8 * j + 6], f[8 * j + 7]));
+          }
         }
-        // 32 columns = 64 bytes = chunks 4*(c&1) .. +3 of the 128-byte row of group c>>1
-        unsigned char* rowp = stg + (c >> 1) * (BM * 128) + r * 128;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int chunk = ((c & 1) * 4 + j) ^ (r & 7);
-          *reinterpret_cast<uint4*>(rowp + chunk * 16) =
-              make_uint4(pack2<T>(f[8 * j], f[8 * j + 1]), pack2<T>(f[8 * j + 2], f[8 * j + 3]),
-                         pack2<T>(f[8 * j + 4], f[8 * j + 5]), pack2<T>(f[8 * j + 6], f[8 * j + 7]));
+        if (sub == 1) {                                            // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[buf]);
         }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);
-      fence_proxy_async_smem();
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + h) : "memory");
-      if (q == 0 && lane == 0) {
-        tma_store_2d(&tmC, stg, n0 + h * 128, m0);
-        tma_store_2d(&tmC, stg + BM * 128, n0 + h * 128 + 64, m0);
-        tma_store_commit();
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + h) : "memory");
+        if (q == 0 && lane == 0) {
+          tma_store_2d(&tmC, stg, n0 + h * 128 + sub * 64, m0);
+          tma_store_commit();
+        }
       }
     }
     if (active && q == 0 && lane == 0) tma_store_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();              // no CTA leaves while its peer may still multicast into it or arrive on its barriers
   if (warp == 2) tmem_dealloc(tmem_base, 2 * BN);
 }
 
-template <typename T, int BN>
+template <typename T, int BN, int NBUF>
 static cudaError_t launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const T* bias, int M, int N,
                              int K, int sms, cudaStream_t st) {
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, NBUF>;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<T, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<T, BN, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  gemm_tn_kernel<T, BN><<<tiles < sms ? tiles : sms, GEMM_THREADS, S::TOTAL, st>>>(tmA, tmB, tmC, bias, M, N, K);
+  const int pairs = (((M + BM - 1) / BM + 1) / 2) * ((N + BN - 1) / BN);
+  const int nclusters = pairs < sms / 2 ? pairs : sms / 2;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * nclusters);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = S::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute lattr[1];
+  lattr[0].id = cudaLaunchAttributeClusterDimension;
+  lattr[0].val.clusterDim.x = 2; lattr[0].val.clusterDim.y = 1; lattr[0].val.clusterDim.z = 1;
+  cfg.attrs = lattr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tn_kernel<T, BN, NBUF>, tmA, tmB, tmC, bias, M, N, K);
+  if (le != cudaSuccess) return le;
   return cudaGetLastError();
 }
 
@@ -212,10 +246,13 @@ int gemm_tn_tc(const T* A, int64_t lda, const T* B, int64_t ldb, T* C, int64_t l
   CUtensorMap tmA, tmB, tmC;
   const int BN = (N > 128) ? 256 : 128;
   if (!make_tmap_2d(&tmA, dt, 2, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK)) return -1;
-  if (!make_tmap_2d(&tmB, dt, 2, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)BN, BK)) return -1;
+  if (!make_tmap_2d(&tmB, dt, 2, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)BN / 2, BK)) return -1;   // half tile per CTA
   if (!make_tmap_2d(&tmC, dt, 2, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, BM, 64)) return -1;
-  cudaError_t e = (BN == 256) ? launch_tn<T, 256>(tmA, tmB, tmC, bias, M, N, K, sms, st)
-                              : launch_tn<T, 128>(tmA, tmB, tmC, bias, M, N, K, sms, st);
+  const bool short_k = K <= 512;
+  cudaError_t e = (BN == 256) ? (short_k ? launch_tn<T, 256, 2>(tmA, tmB, tmC, bias, M, N, K, sms, st)
+                                         : launch_tn<T, 256, 1>(tmA, tmB, tmC, bias, M, N, K, sms, st))
+                              : (short_k ? launch_tn<T, 128, 2>(tmA, tmB, tmC, bias, M, N, K, sms, st)
+                                         : launch_tn<T, 128, 1>(tmA, tmB, tmC, bias, M, N, K, sms, st));
   return e == cudaSuccess ? 0 : -2;
 }
 

@@ -64,6 +64,23 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* desc, ui
       "l"(desc), "r"(smem_u32(bar)), "r"(x), "r"(y)
       : "memory");
 }
+// same, delivered to the same shared-memory offset (and mbarrier offset) of every CTA of the cluster in cta_mask
+__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const void* desc, uint64_t* bar, int x, int y,
+                                                      uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
+      "%4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(desc), "r"(smem_u32(bar)), "r"(x), "r"(y), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const void* desc, const void* smem_src, int x, int y) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(desc),
                "r"(smem_u32(smem_src)), "r"(x), "r"(y)
@@ -91,6 +108,13 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // all prior tcgen05.mma of this thread -> one arrival on the mbarrier when they complete
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// same, arriving on the barrier at this offset in every CTA of cta_mask (stage release in a multicast pipeline)
+__device__ __forceinline__ void tc_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]^T ; one thread issues for the CTA
 __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {

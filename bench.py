@@ -225,7 +225,7 @@ def main():
     d2h = B * (r * (M + N_IN) * 2)
 
     # ---- roofline.  The SVD "kernel" of SURVEY.md 8(d) is the Jacobi round: one launch each of gram_tc_kernel,
-    # solve_kernel and update_tc_kernel; its algorithmic HBM bytes are one read of X (Gram), one read + one write
+    # solve_quad_kernel and update_tc_kernel; its algorithmic HBM bytes are one read of X (Gram), one read + one write
     # of X (update) plus the small Gram / rotation buffers.  Timed with per-class CUDA events (asvd_profile_*)
     # over the first two sweeps, where every block pair is active; per-kernel figures are reported beside it.
     roofline, classes = None, None
@@ -264,12 +264,12 @@ def main():
                                          "dram_traffic_ncu": traffic.get(k) or traffic.get(k + "_tc")}
         bytes_round = sum(alg.values())
         tr = [per_kernel[k + "_kernel"]["dram_traffic_ncu"] for k in ("gram", "solve", "update")]
-        roofline = {"bound": "hbm", "kernel": "jacobi_round = gram_tc_kernel + solve_kernel + update_tc_kernel (one launch each)",
+        roofline = {"bound": "hbm", "kernel": "jacobi_round = gram_tc_kernel + solve_quad_kernel + update_tc_kernel (one launch each)",
                     "achieved": bytes_round / t_round / 1e3, "peak": peak, "unit": "GB/s", "frac": bytes_round / t_round / 1e3 / peak,
                     "traffic": (sum(tr) if all(v is not None for v in tr) else None), "peak_source": which,
                     "algorithmic_bytes_per_launch": bytes_round, "avg_launch_us": round(t_round, 1),
-                    "note": "solve_kernel is an on-chip (shared-memory / register) Jacobi eigensolver: it moves 18 MB per launch and is "
-                            "bounded by its dependent rotation steps, not by HBM; gram/update are the streaming passes",
+                    "note": "solve_quad_kernel is an on-chip (register / shared-memory) Jacobi eigensolver: it moves 42 MB per launch and "
+                            "is bounded by its 127 dependent rotation steps, not by HBM; gram/update are the streaming passes",
                     "per_kernel": per_kernel,
                     "class_ms_first_2_sweeps": {k: round(v["ms"], 3) for k, v in classes.items()},
                     "class_ms_full_factorisation": full_run}
