@@ -71,7 +71,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // contiguous (K) dimension of every dot product.
 constexpr int JB = 64;        // vectors per block
 constexpr int JK = 2 * JB;    // vectors per pair = order of the Gram / rotation matrices
-constexpr int GRAM_CHUNK = 1024;  // columns of X reduced by one Gram CTA
+constexpr int GRAM_CHUNK = 1024;  // columns of X reduced by one Gram work item (512 when that fills the SMs better)
 
 // X is stored BLOCK-TILED in HBM: tile (blk, ct) = 64 vectors x 32 consecutive elements = one contiguous 8 KB chunk,
 // tiles of a block laid out along the vector dimension.  Every TMA box of the streaming passes is then one
@@ -95,7 +95,7 @@ struct SvdPlan {
   int nv_pad;      // multiple of JK
   int len_pad;     // multiple of 128
   int ldy;         // leading dimension of Y rows (length nv, padded to 4)
-  int nb, rounds, pairs, chunks;
+  int nb, rounds, pairs, chunks, chunk_cols;
   // byte offsets into the workspace
   size_t off_ptrs, off_pairs, off_X, off_Xr, off_Y, off_G, off_R, off_flag, off_maxoff, off_done, off_sigma, off_perm,
       off_status, off_scale, off_norm, off_track;

@@ -89,6 +89,9 @@ SvdPlan make_plan(int m, int n, int batch) {
   p.nb = p.nv_pad / JB;
   p.rounds = p.nb - 1;
   p.pairs = p.nb / 2;
+  // (512-column chunks would fill the last wave of the persistent Gram pass better at batch 4 x 4096^2 -- 6.92 waves
+  // instead of 3.46 -- but double the partial-Gram traffic: measured 260.7 vs 259.5 ms, so the width stays fixed.)
+  p.chunk_cols = GRAM_CHUNK;
   p.chunks = (p.len_pad + GRAM_CHUNK - 1) / GRAM_CHUNK;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = (size_t)round_up((int64_t)(off + bytes), 256); return o; };
@@ -153,7 +156,8 @@ __global__ void fill_kernel(float* p, float v, int64_t n) {
 __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, int64_t mat_stride, int ldx,
                                                    const int2* __restrict__ pairs, int len_pad, int chunks,
                                                    int pairs_per_mat, float* __restrict__ Gpart,
-                                                   const int* __restrict__ done, const int* __restrict__ track, int nb) {
+                                                   const int* __restrict__ done, const int* __restrict__ track, int nb,
+                                                   int chunk_cols) {
   __shared__ __align__(16) float As[2][GK][GLD];
   const int b = blockIdx.z, p = blockIdx.y, c = blockIdx.x;
   if (done[b]) return;
@@ -164,7 +168,7 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, 
   const int row = t >> 1, kq = (t & 1) * 8;
   const int vec = (row < JB) ? pr.x * JB + row : pr.y * JB + (row - JB);
   const int nct = ldx >> 5;
-  const int kbeg = c * GRAM_CHUNK, kend = min(len_pad, kbeg + GRAM_CHUNK);
+  const int kbeg = c * chunk_cols, kend = min(len_pad, kbeg + chunk_cols);
   const int nk = (kend - kbeg) / GK;
 
   float acc[8][8];
@@ -1028,9 +1032,9 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
       const int round_stamp = 2 + sweep * p.rounds + r;
       const int half_gram = (use_tc && gram_precise) ? 1 : 0;   // gram_tc_kernel's precise mode stores T, G = T + T^T
       if (use_tc) {
-        ASVD_LAUNCH(K_GRAM, st, ASVD_CUDA_CHECK(tc::launch_gram_tc(tmK, pr, p.pairs, p.chunks, GRAM_CHUNK, p.len_pad, p.nv_pad, p.batch, G, done, gram_precise, track, st)));
+        ASVD_LAUNCH(K_GRAM, st, ASVD_CUDA_CHECK(tc::launch_gram_tc(tmK, pr, p.pairs, p.chunks, p.chunk_cols, p.len_pad, p.nv_pad, p.batch, G, done, gram_precise, track, st)));
       } else {
-        ASVD_LAUNCH(K_GRAM, st, (gram_kernel<<<dim3(p.chunks, p.pairs, p.batch), 256, 0, st>>>(X, xs, p.len_pad, pr, p.len_pad, p.chunks, p.pairs, G, done, track, p.nb)));
+        ASVD_LAUNCH(K_GRAM, st, (gram_kernel<<<dim3(p.chunks, p.pairs, p.batch), 256, 0, st>>>(X, xs, p.len_pad, pr, p.len_pad, p.chunks, p.pairs, G, done, track, p.nb, p.chunk_cols)));
       }
       if (solve_quad)
         ASVD_LAUNCH(K_SOLVE, st, (solve_quad_kernel<<<dim3(p.pairs, p.batch), SOLVE_THREADS, SOLVEQ_SMEM, st>>>(G, p.chunks, p.pairs, R, flag, maxoff, status, done, tol, polish_flag, pr, track, p.nb, round_stamp, gram_precise, half_gram)));

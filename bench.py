@@ -246,9 +246,12 @@ def main():
         _lib.profile_enable(False)
         full_run = {k: round(after[k][0], 2) for k in after if after[k][1] > before[k][1]}
         nv = len_ = 4096
-        pairs, chunks, JK = nv // 128, len_ // 1024, 128
+        # algorithmic bytes: X is read once by the Gram pass and read + written once by the update; one
+        # 128x128 Gram matrix and one rotation per block pair go between the passes.  (The implementation writes its Gram
+        # matrices as 4-8 partial sums per pair; that extra traffic is not counted as useful work.)
+        pairs, JK = nv // 128, 128
         x_bytes = B * nv * len_ * 4
-        g_bytes, r_bytes = B * pairs * chunks * JK * JK * 4, B * pairs * JK * JK * 4
+        g_bytes = r_bytes = B * pairs * JK * JK * 4
         alg = {"gram": x_bytes + g_bytes, "solve": g_bytes + r_bytes, "update": 2 * x_bytes + r_bytes}
         peak, which = peaks()
         traffic = {}
