@@ -84,9 +84,10 @@ def main():
                            "kept_energy_rel_err": abs(kept[0] - kept[1]) / kept[1], "sweeps": sweeps_seen.get((m, n))})
             del fact, A, B, AB, An
     if dist is not None:
+        dt_local = dt
         t = torch.tensor([dt], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
         gathered = [None] * world
-        dist.all_gather_object(gathered, {"rank": rank, "matrices": done, "seconds": time.perf_counter() - t0, "per_shape": per_shape, "checks": checks})
+        dist.all_gather_object(gathered, {"rank": rank, "matrices": done, "seconds": dt_local, "per_shape": per_shape, "checks": checks})
     else:
         gathered = [{"rank": 0, "matrices": done, "seconds": dt, "per_shape": per_shape, "checks": checks}]
     if rank == 0:
