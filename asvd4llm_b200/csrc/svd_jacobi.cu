@@ -89,10 +89,25 @@ SvdPlan make_plan(int m, int n, int batch) {
   p.nb = p.nv_pad / JB;
   p.rounds = p.nb - 1;
   p.pairs = p.nb / 2;
-  // (512-column chunks would fill the last wave of the persistent Gram pass better at batch 4 x 4096^2 -- 6.92 waves
-  // instead of 3.46 -- but double the partial-Gram traffic: measured 260.7 vs 259.5 ms, so the width stays fixed.)
-  p.chunk_cols = GRAM_CHUNK;
-  p.chunks = (p.len_pad + GRAM_CHUNK - 1) / GRAM_CHUNK;
+  {
+    // Gram work items = batch * pairs * chunks.  One wave of items that each reduce a long run of columns beats many
+    // short ones: every item ends with a 64 KB partial Gram that the solve kernel has to read back and sum (measured
+    // at batch 4 x 4096^2: 512-column chunks 260.7 ms, 1024-column chunks 259.5 ms).  So: just enough chunks to
+    // give every SM an item, never narrower than 512 columns.
+    static int sms = 0;
+    if (!sms) {
+      int dev = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+        sms = 148;
+      cudaGetLastError();
+    }
+    int want = sms / (batch * p.pairs > 0 ? batch * p.pairs : 1);
+    const int max_chunks = (p.len_pad + 511) / 512;
+    if (want < 1) want = 1;
+    if (want > max_chunks) want = max_chunks;
+    p.chunk_cols = (int)round_up((p.len_pad + want - 1) / want, 32);
+    p.chunks = (p.len_pad + p.chunk_cols - 1) / p.chunk_cols;
+  }
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = (size_t)round_up((int64_t)(off + bytes), 256); return o; };
   p.off_ptrs = take(sizeof(void*) * 2 * (size_t)batch);
