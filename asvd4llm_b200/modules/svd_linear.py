@@ -160,6 +160,7 @@ def from_linear_batch(linears: Sequence[nn.Linear], param_ratios: Sequence[float
         if len(linears) == 1:
             _CACHE.update(key=_key(linears[0], act_aware, alpha), fact=fact)
     out = []
+    pending_host = False
     for b, (lin, r) in enumerate(zip(linears, ranks)):
         if fact is None:
             print("nan in S")                                    # upstream message (:82)
@@ -168,7 +169,19 @@ def from_linear_batch(linears: Sequence[nn.Linear], param_ratios: Sequence[float
         w = lin.weight.data
         A, B = fact.extract(r, sigma_fuse, w.dtype, b)
         if A.device != w.device:
-            A, B = A.to(w.device), B.to(w.device)
+            if w.device.type == "cpu":
+                # host-resident model: the factors go back through pinned buffers, all copies queued behind the
+                # extraction kernels and awaited once (a pageable .to("cpu") per tensor costs 3x the copy time)
+                Ah = torch.empty(A.shape, dtype=A.dtype, pin_memory=True)
+                Bh = torch.empty(B.shape, dtype=B.dtype, pin_memory=True)
+                Ah.copy_(A, non_blocking=True)
+                Bh.copy_(B, non_blocking=True)
+                A, B = Ah, Bh
+                pending_host = True
+            else:
+                A, B = A.to(w.device), B.to(w.device)
         bias = lin.bias.data if lin.bias is not None else None
         out.append(SVDLinear._from_factors(A, B, bias))
+    if pending_host:
+        torch.cuda.current_stream(dev).synchronize()
     return out
