@@ -333,3 +333,44 @@ def test_rectangular_llama_shapes_reduced():
     for (m, n) in [(1376, 512), (512, 1376), (4000, 512)]:
         W, s = O.synthetic_weight(m, n, seed=5)
         check_factorisation(W, (s ** 0.5 + 1e-6).float(), 0.9, "UV")
+
+
+def test_inner_orderings_and_tails_agree(monkeypatch):
+    """The two inner eigen-solvers (quad round-robin / odd-even) and the two tails (unit column norms /
+    Newton-Schulz) are different routes to the same factorisation: singular values and the truncated product agree."""
+    L = _lib()
+    W, s = O.synthetic_weight(1024, 1024, seed=11)
+    scale = (s ** 0.5 + 1e-6).float().cuda()
+    ref = torch.linalg.svdvals(W.double().cuda() * scale.double())
+    results = {}
+    for solve, polish in (("quad", "norm"), ("oddeven", "norm"), ("quad", "NS"), ("oddeven", "NS")):
+        monkeypatch.setenv("ASVD_B200_SOLVE", solve)
+        monkeypatch.setenv("ASVD_B200_POLISH", polish)
+        f = L.scaled_svd([W.cuda()], [scale])
+        assert f.status == 0
+        sig = f.sigma().double()
+        assert ((sig[:460] - ref[:460]).abs() / ref[:460]).max().item() < 2e-5, (solve, polish)
+        A, B = f.extract(460, "UV", torch.float32)
+        results[(solve, polish)] = (A @ B) * scale
+    monkeypatch.delenv("ASVD_B200_SOLVE")
+    monkeypatch.delenv("ASVD_B200_POLISH")
+    base = results[("quad", "norm")]
+    for k, v in results.items():
+        assert (v - base).norm().item() / base.norm().item() < 5e-4, k
+
+
+def test_llama13b_block_counts_reduced():
+    """5120-wide layers give 80 blocks of 64 vectors (not a power of two) and 40 pairs per round; same structure at
+    1/8 scale: 640 vectors = 10 blocks, plus the 2.7:1 rectangles of the 13B MLP."""
+    for (m, n) in [(640, 640), (1728, 640), (640, 1728)]:
+        W, s = O.synthetic_weight(m, n, seed=9)
+        check_factorisation(W, (s ** 0.5 + 1e-6).float(), 0.95, "UV")
+
+
+def test_suggest_batch_fills_one_wave():
+    L = _lib()
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    for (m, n) in [(4096, 4096), (11008, 4096), (768, 768), (5120, 5120)]:
+        b = L.suggest_batch(m, n)
+        pairs = (min(m, n) + 127) // 128
+        assert 1 <= b <= 32 and b * pairs <= max(sms, pairs)
