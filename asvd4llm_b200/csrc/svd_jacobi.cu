@@ -135,9 +135,11 @@ SvdPlan make_plan(int m, int n, int batch) {
 template <typename T>
 __global__ void __launch_bounds__(256) prep_kernel(const void* const* __restrict__ Wptrs, const float* __restrict__ scale,
                                                    int64_t ldw, int m, int n, int tall, float* __restrict__ X,
-                                                   int64_t mat_stride, int ldx) {
+                                                   int64_t mat_stride, int ldx, const int* __restrict__ slot, int nv_pad) {
+  // slot (optional): row of X that vector v goes to (the ascending-norm order of presort_*), per matrix [nv_pad]
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
+  const int* sl = slot ? slot + (int64_t)b * nv_pad : nullptr;
   const T* W = reinterpret_cast<const T*>(Wptrs[b]);
   const float* s = scale + (int64_t)b * n;
   float* Xb = X + b * mat_stride;
@@ -151,14 +153,57 @@ __global__ void __launch_bounds__(256) prep_kernel(const void* const* __restrict
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {
       int j = j0 + r, i = i0 + tx;
-      if (j < n && i < m) Xb[xt_off(j, i, ldx >> 5)] = tile[tx][r];
+      if (j < n && i < m) Xb[xt_off(sl ? sl[j] : j, i, ldx >> 5)] = tile[tx][r];
     }
   } else {
     for (int r = ty; r < 32; r += 8) {
       int i = i0 + r, j = j0 + tx;
-      if (i < m && j < n) Xb[xt_off(i, j, ldx >> 5)] = to_f32<T>(W[(int64_t)i * ldw + j]) * s[j];
+      if (i < m && j < n) Xb[xt_off(sl ? sl[i] : i, j, ldx >> 5)] = to_f32<T>(W[(int64_t)i * ldw + j]) * s[j];
     }
   }
+}
+
+// Sort keys for the initial order of the vectors: key = 1 / |vector|^2, so the descending sort_kernel below puts the
+// vectors in ASCENDING norm order (zero padding keys sort last).  Which vector sits in which row of X is immaterial to
+// the result; measured on the scaled Gaussian workload this order saves about one sweep in 15 (4096^2: 254.6 -> 246.2
+// ms per batch of four; 11008x4096: 410.9 -> 399.1 ms).  Fixed summation order: results stay run-to-run bitwise equal.
+template <typename T>
+__global__ void __launch_bounds__(256) presort_key_kernel(const void* const* __restrict__ Wptrs, const float* __restrict__ scale,
+                                                          int64_t ldw, int m, int n, int tall, float* __restrict__ key,
+                                                          int nv_pad) {
+  const int b = blockIdx.y;
+  const T* W = reinterpret_cast<const T*>(Wptrs[b]);
+  const float* s = scale + (int64_t)b * n;
+  float* kb = key + (int64_t)b * nv_pad;
+  __shared__ float part[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (tall) {                       // vector j = column j of W * s: 32 columns per CTA, rows split over the 8 warps
+    const int j = blockIdx.x * 32 + tx;
+    float ss = 0.f;
+    if (j < n)
+      for (int i = ty; i < m; i += 8) { const float x = to_f32<T>(W[(int64_t)i * ldw + j]); ss = fmaf(x, x, ss); }
+    part[ty][tx] = ss;
+    __syncthreads();
+    if (ty == 0 && j < n) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += part[w][tx];
+      t *= s[j] * s[j];
+      kb[j] = t > 0.f ? 1.f / t : 0.f;
+    }
+  } else {                          // vector i = row i of W * diag(s): one warp per row, 8 rows per CTA
+    const int i = blockIdx.x * 8 + ty;
+    float ss = 0.f;
+    if (i < m)
+      for (int l = tx; l < n; l += 32) { const float x = to_f32<T>(W[(int64_t)i * ldw + l]) * s[l]; ss = fmaf(x, x, ss); }
+    ss = warp_sum(ss);
+    if (tx == 0 && i < m) kb[i] = ss > 0.f ? 1.f / ss : 0.f;
+  }
+}
+// perm[r] = vector placed in row r  ->  slot[vector] = r
+__global__ void presort_slot_kernel(const int* __restrict__ perm, int* __restrict__ slot, int nv_pad) {
+  const int b = blockIdx.y, r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < nv_pad) slot[(int64_t)b * nv_pad + perm[(int64_t)b * nv_pad + r]] = r;
 }
 
 __global__ void fill_kernel(float* p, float v, int64_t n) {
@@ -1004,8 +1049,22 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
     ASVD_CUDA_CHECK(cudaStreamSynchronize(st));
   }
   {
+    // initial order of the vectors: ascending norm (ASVD_B200_PRESORT=0 keeps the given order).  sigma / norm / perm are
+    // free until the epilogue; the slot table lives in the (not yet used) Y buffer.
+    const char* ps_env = getenv("ASVD_B200_PRESORT");
+    int* slot = nullptr;
+    if (!(ps_env && ps_env[0] == '0')) {
+      slot = reinterpret_cast<int*>(Y);
+      ASVD_CUDA_CHECK(cudaMemsetAsync(sigma, 0, sizeof(float) * p.batch * p.nv_pad, st));
+      dim3 gk(p.tall ? (p.n + 31) / 32 : (p.m + 7) / 8, p.batch);
+      ASVD_LAUNCH(K_PREP, st, (presort_key_kernel<T><<<gk, 256, 0, st>>>(d_W, scale, ldw, p.m, p.n, p.tall, sigma, p.nv_pad)));
+      int P = 1;
+      while (P < p.nv_pad) P <<= 1;
+      ASVD_LAUNCH(K_PREP, st, (sort_kernel<<<p.batch, 1024, 8 * (size_t)P, st>>>(sigma, norm, perm, p.nv, p.nv_pad, P)));
+      ASVD_LAUNCH(K_PREP, st, (presort_slot_kernel<<<dim3((p.nv_pad + 255) / 256, p.batch), 256, 0, st>>>(perm, slot, p.nv_pad)));
+    }
     dim3 grid((p.n + 31) / 32, (p.m + 31) / 32, p.batch);
-    ASVD_LAUNCH(K_PREP, st, (prep_kernel<T><<<grid, 256, 0, st>>>(d_W, scale, ldw, p.m, p.n, p.tall, X, xs, p.len_pad)));
+    ASVD_LAUNCH(K_PREP, st, (prep_kernel<T><<<grid, 256, 0, st>>>(d_W, scale, ldw, p.m, p.n, p.tall, X, xs, p.len_pad, slot, p.nv_pad)));
     ASVD_CUDA_CHECK(cudaGetLastError());
   }
   // ASVD_B200_SIMT=1 selects the fp32 SIMT Gram / update kernels (kept as the in-library reference the
