@@ -51,10 +51,20 @@ template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, fl
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <typename T, int BN, int NBUF>
+// K schedule: the contraction runs over nseg segments of nk k-steps; segment s reads A columns a_off[s] + k and B
+// columns b_off[s] + k.  A plain GEMM is one segment at offset 0.  The recovery GEMM of the SVD (fp32 x 16-bit product
+// evaluated exactly with bf16 planes: A = [a1|a2|a3], B = [b1|b2]) runs a1 b1 + a2 b1 + a3 b1 + a1 b2 + a2 b2 as five
+// segments accumulating into the same TMEM tile.
+struct KSched {
+  int nseg, nk;
+  int a_off[6], b_off[6];
+};
+
+template <typename T, int BN, int NBUF, bool F32OUT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const T* __restrict__ bias, int M, int N, int K) {
+               const __grid_constant__ CUtensorMap tmC, const T* __restrict__ bias, int M, int N, int K,
+               float* __restrict__ Cf, int64_t ldcf, const float* __restrict__ cscale, const KSched ks) {
   using S = GemmSmem<BN, NBUF>;
   constexpr int STAGES = S::STAGES;
   extern __shared__ unsigned char smem_dyn[];
@@ -68,14 +78,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
   const int num_tiles = ((num_m + 1) / 2) * num_n;          // pairs of vertically adjacent tiles, one pair per cluster
-  const int num_k = (K + BK - 1) / BK;
+  const int num_k = ks.nseg * ks.nk;
   const int crank = (int)cluster_ctarank();
   const int cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    tma_prefetch_desc(&tmC);
+    if (!F32OUT) tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 2); }
@@ -98,9 +108,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty[stage], phase ^ 1);
           unsigned char* a = smem + stage * S::STAGE_BYTES;
           mbar_arrive_expect_tx(&full[stage], S::STAGE_BYTES);     // own A tile + both halves of the B tile
-          tma_load_2d(a, &tmA, &full[stage], k * BK, m0);
-          tma_load_2d_multicast(a + S::A_BYTES + crank * (S::B_BYTES / 2), &tmB, &full[stage], k * BK, n0 + crank * (BN / 2),
-                                (uint16_t)3);
+          const int seg = k / ks.nk, kk = (k - seg * ks.nk) * BK;
+          tma_load_2d(a, &tmA, &full[stage], ks.a_off[seg] + kk, m0);
+          tma_load_2d_multicast(a + S::A_BYTES + crank * (S::B_BYTES / 2), &tmB, &full[stage], ks.b_off[seg] + kk,
+                                n0 + crank * (BN / 2), (uint16_t)3);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -150,6 +161,40 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (!active) continue;
       mbar_wait(&tfull[buf], use & 1);
       tc_fence_after();
+      if constexpr (F32OUT) {
+        // fp32 result straight from the accumulator to global memory (each thread owns a row: 128 contiguous bytes per
+        // 32-column step), optionally scaled per column
+        const int row = m0 + r;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + h * 128 + c * 32), v);
+          tmem_ld_wait();
+          const int col0 = n0 + h * 128 + c * 32;
+          if (row < M) {
+            float* dst = Cf + (int64_t)row * ldcf + col0;
+            if (col0 + 32 <= N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                       __uint_as_float(v[4 * j + 3]));
+                if (cscale) {
+                  const float4 sc = *reinterpret_cast<const float4*>(cscale + col0 + 4 * j);
+                  o.x *= sc.x; o.y *= sc.y; o.z *= sc.z; o.w *= sc.w;
+                }
+                reinterpret_cast<float4*>(dst)[j] = o;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < N) dst[j] = __uint_as_float(v[j]) * (cscale ? cscale[col0 + j] : 1.f);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[buf]);
+      } else {
 #pragma unroll 1
       for (int sub = 0; sub < 2; ++sub) {                          // 64 columns at a time through a 16 KB staging buffer
         // the store that last used this staging buffer must have finished reading it
@@ -193,8 +238,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tma_store_commit();
         }
       }
+      }
     }
-    if (active && q == 0 && lane == 0) tma_store_wait<0>();
+    if (!F32OUT && active && q == 0 && lane == 0) tma_store_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -202,13 +248,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 2) tmem_dealloc(tmem_base, 2 * BN);
 }
 
-template <typename T, int BN, int NBUF>
+template <typename T, int BN, int NBUF, bool F32OUT = false>
 static cudaError_t launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const T* bias, int M, int N,
-                             int K, int sms, cudaStream_t st) {
+                             int K, int sms, cudaStream_t st, float* Cf = nullptr, int64_t ldcf = 0, const float* cscale = nullptr,
+                             const KSched* sched = nullptr) {
   using S = GemmSmem<BN, NBUF>;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<T, BN, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<T, BN, NBUF, F32OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     if (e != cudaSuccess) return e;
     attr = true;
   }
@@ -225,7 +272,10 @@ static cudaError_t launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, con
   lattr[0].val.clusterDim.x = 2; lattr[0].val.clusterDim.y = 1; lattr[0].val.clusterDim.z = 1;
   cfg.attrs = lattr;
   cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tn_kernel<T, BN, NBUF>, tmA, tmB, tmC, bias, M, N, K);
+  KSched ks;
+  if (sched) ks = *sched;
+  else { memset(&ks, 0, sizeof(ks)); ks.nseg = 1; ks.nk = (K + BK - 1) / BK; }
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tn_kernel<T, BN, NBUF, F32OUT>, tmA, tmB, tmC, bias, M, N, K, Cf, ldcf, cscale, ks);
   if (le != cudaSuccess) return le;
   return cudaGetLastError();
 }
@@ -253,6 +303,45 @@ int gemm_tn_tc(const T* A, int64_t lda, const T* B, int64_t ldb, T* C, int64_t l
                                          : launch_tn<T, 256, 1>(tmA, tmB, tmC, bias, M, N, K, sms, st))
                               : (short_k ? launch_tn<T, 128, 2>(tmA, tmB, tmC, bias, M, N, K, sms, st)
                                          : launch_tn<T, 128, 1>(tmA, tmB, tmC, bias, M, N, K, sms, st));
+  return e == cudaSuccess ? 0 : -2;
+}
+
+// C[M,N] (fp32, overwritten) = sum over plane pairs of A_i[:, k] * B_j[:, k]^T for k in [k_begin, k_begin + k_len), bf16 planes
+int gemm_planes_f32(const __nv_bfloat16* A, int64_t lda, int a_planes, const __nv_bfloat16* B, int64_t ldb, int b_planes,
+                    float* C, int64_t ldc, int M, int N, int kseg, int k_begin, int k_len, const float* cscale,
+                    cudaStream_t st) {
+  auto ok = [](const void* p, int64_t ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld * 2) % 16 == 0; };
+  if (!ok(A, lda) || !ok(B, ldb) || kseg % BK != 0 || k_begin % BK != 0 || k_len % BK != 0 || k_len <= 0 || k_begin + k_len > kseg ||
+      a_planes < 1 || a_planes > 3 || b_planes < 1 || b_planes > 2)
+    return 1;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  CUtensorMap tmA, tmB, tmC;
+  constexpr int BN = 256;
+  if (!make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, (uint64_t)M, (uint64_t)a_planes * kseg, (uint64_t)lda, BM, BK)) return -1;
+  if (!make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, (uint64_t)N, (uint64_t)b_planes * kseg, (uint64_t)ldb, BN / 2, BK)) return -1;
+  tmC = tmA;                                   // unused by the fp32 epilogue
+  // Plane products a_i b_j with i + j <= 2 (the others are below fp32 resolution: 2^-8(i+j) relative), SMALLEST FIRST.
+  // The tensor core adds each K = 16 group of products into the fp32 accumulator with truncation, about half an ulp of
+  // the accumulator per instruction and always the same way: with the leading a1 b1 segment first, the 1280
+  // instructions of a 4096-long contraction biased sigma by 4e-5..5e-4 relative (measured against fp64).  Accumulating
+  // the correction planes while the accumulator is still small leaves only the 256 instructions of a1 b1 at full
+  // magnitude -- and the caller splits long contractions into runs of at most ~1024 (k_begin, k_len), one fp32 partial
+  // result each, summed with ordinary rounding afterwards.
+  KSched ks;
+  memset(&ks, 0, sizeof(ks));
+  ks.nk = k_len / BK;
+  for (int sum = 2; sum >= 0; --sum)
+    for (int j = b_planes - 1; j >= 0; --j) {
+      const int i = sum - j;
+      if (i < 0 || i >= a_planes || ks.nseg >= 6) continue;
+      ks.a_off[ks.nseg] = i * kseg + k_begin; ks.b_off[ks.nseg] = j * kseg + k_begin; ++ks.nseg;
+    }
+  cudaError_t e = launch_tn<__nv_bfloat16, BN, 1, true>(tmA, tmB, tmC, nullptr, M, N, kseg, sms, st, C, ldc, cscale, &ks);
   return e == cudaSuccess ? 0 : -2;
 }
 

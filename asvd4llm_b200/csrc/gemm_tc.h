@@ -1,6 +1,7 @@
 // tcgen05 GEMM entry (gemm_tc.cu): C[M,N] = A[M,K] B[N,K]^T + bias, 16-bit operands, fp32 accumulation.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 namespace asvd {
 namespace tc {
@@ -8,5 +9,9 @@ namespace tc {
 template <typename T>
 int gemm_tn_tc(const T* A, int64_t lda, const T* B, int64_t ldb, T* C, int64_t ldc, const T* bias, int M, int N, int K,
                cudaStream_t st);
+// fp32 C[M,N] = sum of bf16 plane products (see KSched in gemm_tc.cu): A = [a1|a2|a3] (a_planes x kseg columns),
+// B = [b1|b2]; optional per-column scale.  0 = launched, 1 = operands not eligible, < 0 = error
+int gemm_planes_f32(const __nv_bfloat16* A, int64_t lda, int a_planes, const __nv_bfloat16* B, int64_t ldb, int b_planes,
+                    float* C, int64_t ldc, int M, int N, int kseg, int k_begin, int k_len, const float* cscale, cudaStream_t st);
 }  // namespace tc
 }  // namespace asvd

@@ -15,12 +15,14 @@
 // The second factor is NOT accumulated: it is recovered from the ORIGINAL weight with one fp32 GEMM
 // (Y = Xhat * W*diag(s)), which also anchors sigma_j = |Y_j| to the input and removes accumulated drift.
 #include <stdarg.h>
+#include <type_traits>
 #include <float.h>
 #include <vector>
 #include <atomic>
 #include <utility>
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tc.h"
 #include "svd_tc.h"
 #include "umma.cuh"
 #include <stdlib.h>
@@ -76,6 +78,8 @@ double prof_ms(int k) { return g_prof_ms[k]; }
 unsigned long long launches(int k) { return g_launches[k].load(); }
 
 // ------------------------------------------------------------------------------------------------ plan
+constexpr int RECOVER_MAX_SPLITS = 16;     // K splits of the tensor-core recovery GEMM (runs of <= 1024 columns)
+constexpr int RECOVER_RUN = 768;
 SvdPlan make_plan(int m, int n, int batch) {
   SvdPlan p;
   memset(&p, 0, sizeof(p));
@@ -126,6 +130,11 @@ SvdPlan make_plan(int m, int n, int batch) {
   p.off_scale = take(sizeof(float) * (size_t)batch * n);
   p.off_norm = take(sizeof(float) * (size_t)batch * p.nv_pad);
   p.off_track = take(sizeof(int) * (size_t)batch * (p.nb + (size_t)p.nb * p.nb));
+  // scratch of the tensor-core recovery GEMM, one matrix at a time: bf16 planes [a1|a2|a3] of the normalised vectors
+  // and [b1|b2] of the weight (transposed when the vectors are its columns)
+  p.off_As = take(sizeof(__nv_bfloat16) * 3 * (size_t)p.nv_pad * p.len_pad);
+  p.off_Bs = take(sizeof(__nv_bfloat16) * 2 * (size_t)p.nv_pad * p.len_pad);
+  p.off_Yp = take(sizeof(float) * RECOVER_MAX_SPLITS * (size_t)p.nv_pad * p.ldy);    // fp32 partial results of the K splits
   p.bytes = off;
   return p;
 }
@@ -947,6 +956,91 @@ __global__ void __launch_bounds__(1024) sort_kernel(const float* __restrict__ si
   }
 }
 
+// ------------------------------------------------------------------------------------------------ recovery planes
+// Y = Xhat * (W diag(s)) has to be as exact as an fp32 product (it anchors sigma and the second factor to the input).
+// On the tensor cores: Xhat (fp32) = a1 + a2 + a3 and W (fp16: 11 significant bits) = b1 + b2 exactly, all bf16, every
+// plane product is exact in the fp32 accumulator, and a1 b1 + a2 b1 + a3 b1 + a1 b2 + a2 b2 drops only terms below
+// 2^-24 (gemm_planes_f32).  The scale is folded into Xhat when it runs along the contraction (wide weights) and into the
+// GEMM epilogue otherwise.
+__device__ __forceinline__ void bf16_planes3(float x, __nv_bfloat16& a1, __nv_bfloat16& a2, __nv_bfloat16& a3) {
+  a1 = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(a1);
+  a2 = __float2bfloat16_rn(r1);
+  a3 = __float2bfloat16_rn(r1 - __bfloat162float(a2));
+}
+__global__ void __launch_bounds__(256) split_x_kernel(const float* __restrict__ Xr, const float* __restrict__ ascale, int nv_pad,
+                                                      int len_pad, int len, __nv_bfloat16* __restrict__ As) {
+  const int row = blockIdx.y;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c >= len_pad) return;
+  const float4 x = *reinterpret_cast<const float4*>(Xr + (int64_t)row * len_pad + c);
+  float v[4] = {x.x, x.y, x.z, x.w};
+  __nv_bfloat16 pl[3][4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (ascale) v[e] = (c + e < len) ? v[e] * ascale[c + e] : 0.f;
+    bf16_planes3(v[e], pl[0][e], pl[1][e], pl[2][e]);
+  }
+  __nv_bfloat16* dst = As + (int64_t)row * (3 * (int64_t)len_pad) + c;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) *reinterpret_cast<uint2*>(dst + (int64_t)q * len_pad) = *reinterpret_cast<uint2*>(pl[q]);
+}
+// planes [b1|b2] of the weight, one row per OUTPUT index of the recovery GEMM (= vector index), contraction index along
+// the row: transposed copy when the vectors are the columns of W (tall), plain copy otherwise
+template <typename T>
+__global__ void __launch_bounds__(256) split_w_kernel(const T* __restrict__ W, int64_t ldw, int m, int n, int tall, int len_pad,
+                                                      __nv_bfloat16* __restrict__ Bs) {
+  __shared__ float tile[32][33];
+  const int j0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t ldb = 2 * (int64_t)len_pad;
+  if (tall) {
+    for (int r = ty; r < 32; r += 8) {
+      const int i = i0 + r, j = j0 + tx;
+      tile[r][tx] = (i < m && j < n) ? to_f32<T>(W[(int64_t)i * ldw + j]) : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+      const int j = j0 + r, i = i0 + tx;
+      if (j < n && i < m) {
+        const float w = tile[tx][r];
+        const __nv_bfloat16 b1 = __float2bfloat16_rn(w);
+        Bs[(int64_t)j * ldb + i] = b1;
+        Bs[(int64_t)j * ldb + len_pad + i] = __float2bfloat16_rn(w - __bfloat162float(b1));
+      }
+    }
+  } else {
+    for (int r = ty; r < 32; r += 8) {
+      const int i = i0 + r, j = j0 + tx;
+      if (i < m && j < n) {
+        const float w = to_f32<T>(W[(int64_t)i * ldw + j]);
+        const __nv_bfloat16 b1 = __float2bfloat16_rn(w);
+        Bs[(int64_t)i * ldb + j] = b1;
+        Bs[(int64_t)i * ldb + len_pad + j] = __float2bfloat16_rn(w - __bfloat162float(b1));
+      }
+    }
+  }
+}
+
+// Y = (sum of the K-split partial results, fixed order) * column scale
+__global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ Yp, int nsplit, int64_t split_stride,
+                                                           float* __restrict__ Y, int64_t total, int ldy,
+                                                           const float* __restrict__ cscale, int ncols) {
+  const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (e >= total) return;
+  float4 acc = *reinterpret_cast<const float4*>(Yp + e);
+  for (int q = 1; q < nsplit; ++q) {
+    const float4 v = *reinterpret_cast<const float4*>(Yp + q * split_stride + e);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  if (cscale) {
+    const int c = (int)(e % ldy);
+    acc.x *= c < ncols ? cscale[c] : 0.f; acc.y *= c + 1 < ncols ? cscale[c + 1] : 0.f;
+    acc.z *= c + 2 < ncols ? cscale[c + 2] : 0.f; acc.w *= c + 3 < ncols ? cscale[c + 3] : 0.f;
+  }
+  *reinterpret_cast<float4*>(Y + e) = acc;
+}
+
 // ------------------------------------------------------------------------------------------------ extract (a5, a6)
 __device__ __forceinline__ float sig_pow(float s, float e) {
   if (!(s > 0.f)) return 0.f;
@@ -1009,7 +1103,7 @@ static void build_pair_table(const SvdPlan& p, std::vector<int2>& tab) {
 
 template <typename T>
 static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, int max_sweeps, int* sweeps_out,
-                   cudaStream_t st) {
+                   cudaStream_t st, const void* const* h_W) {
   const void* const* d_W = reinterpret_cast<const void* const*>(ws + p.off_ptrs);
   const int2* d_pairs = reinterpret_cast<const int2*>(ws + p.off_pairs);
   float* X = reinterpret_cast<float*>(ws + p.off_X);
@@ -1166,11 +1260,44 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
     ASVD_CUDA_CHECK(cudaMemsetAsync(Y, 0, sizeof(float) * gb.strideC * p.batch, st));
     // per-matrix scale vectors live contiguously in the workspace: pass through pointer-free strides by
     // launching one GEMM per matrix when scales differ (batch is small); z-batched otherwise.
+    // 16-bit weights: tensor-core plane GEMM (ASVD_B200_RECOVER=simt keeps the fp32 SIMT GEMM, which fp32 weights
+    // always use)
+    const char* rec_env = getenv("ASVD_B200_RECOVER");
+    const bool recover_tc = use_tc && !std::is_same<T, float>::value && !(rec_env && rec_env[0] == 's') &&
+                            p.len_pad <= RECOVER_MAX_SPLITS * 1024;      // longer vectors: runs would exceed 1024 columns
+    __nv_bfloat16* As = reinterpret_cast<__nv_bfloat16*>(ws + p.off_As);
+    __nv_bfloat16* Bs = reinterpret_cast<__nv_bfloat16*>(ws + p.off_Bs);
+    if (recover_tc) ASVD_CUDA_CHECK(cudaMemsetAsync(Bs, 0, sizeof(__nv_bfloat16) * 2 * (size_t)p.nv_pad * p.len_pad, st));
     for (int b = 0; b < p.batch; ++b) {
       GemmBatch g1 = gb;
       g1.Bptrs = d_W + b;
       const float* sb = scale + (int64_t)b * p.n;
       cudaError_t e;
+      if (recover_tc) {
+        prof_begin(K_FINAL, st);
+        split_x_kernel<<<dim3((p.len_pad / 4 + 255) / 256, p.nv_pad), 256, 0, st>>>(Xr + b * xs, p.tall ? nullptr : sb, p.nv_pad,
+                                                                                 p.len_pad, p.len, As);
+        split_w_kernel<T><<<dim3((p.n + 31) / 32, (p.m + 31) / 32), 256, 0, st>>>(reinterpret_cast<const T*>(h_W[b]), ldw, p.m, p.n,
+                                                                                 p.tall, p.len_pad, Bs);
+        // the contraction is cut into runs of ~768 columns, each into its own fp32 partial result (see gemm_planes_f32
+        // on the truncating accumulation of the tensor core), summed afterwards in a fixed order
+        int nsplit = (p.len_pad + RECOVER_RUN - 1) / RECOVER_RUN;
+        if (nsplit > RECOVER_MAX_SPLITS) nsplit = RECOVER_MAX_SPLITS;
+        const int run = (int)round_up((p.len_pad + nsplit - 1) / nsplit, 64);
+        float* Yp = reinterpret_cast<float*>(ws + p.off_Yp);
+        const int64_t ystride = (int64_t)p.nv_pad * p.ldy;
+        int rc = 0, used = 0;
+        for (int k0 = 0; k0 < p.len_pad && rc == 0; k0 += run, ++used)
+          rc = tc::gemm_planes_f32(As, 3 * (int64_t)p.len_pad, 3, Bs, 2 * (int64_t)p.len_pad,
+                                   std::is_same<T, __nv_bfloat16>::value ? 1 : 2, Yp + used * ystride, p.ldy, p.nv_pad, p.nv,
+                                   p.len_pad, k0, (p.len_pad - k0 < run) ? p.len_pad - k0 : run, nullptr, st);
+        if (rc == 0)
+          sum_partials_kernel<<<(unsigned)((ystride / 4 + 255) / 256), 256, 0, st>>>(Yp, used, ystride, Y + b * gb.strideC, ystride,
+                                                                                 p.ldy, p.tall ? sb : nullptr, p.nv);
+        prof_end(K_FINAL, st);
+        if (rc < 0) { set_error("recovery GEMM launch failed (%d)", rc); return ASVD_ERR_CUDA; }
+        if (rc == 0) continue;
+      }
       prof_begin(K_FINAL, st);
       if (p.tall)   // Y[j][l] = sum_i Xhat[j][i] W[i][l] * s[l]
         e = launch_gemm128<float, T, float, true>(Xr + b * xs, p.len_pad, (const T*)nullptr, ldw, Y + b * gb.strideC, p.ldy,
@@ -1302,9 +1429,9 @@ int asvd_scaled_svd(const void* const* W_host_ptrs, int w_dtype, int64_t ldw, in
   // the pageable host buffers above must outlive the async copies
   ASVD_CUDA_CHECK(cudaStreamSynchronize(st));
   switch (w_dtype) {
-    case ASVD_F32: return run_svd<float>(p, ldw, ws, tol, max_sweeps, sweeps_out_host, st);
-    case ASVD_F16: return run_svd<__half>(p, ldw, ws, tol, max_sweeps, sweeps_out_host, st);
-    default: return run_svd<__nv_bfloat16>(p, ldw, ws, tol, max_sweeps, sweeps_out_host, st);
+    case ASVD_F32: return run_svd<float>(p, ldw, ws, tol, max_sweeps, sweeps_out_host, st, ptrs.data());
+    case ASVD_F16: return run_svd<__half>(p, ldw, ws, tol, max_sweeps, sweeps_out_host, st, ptrs.data());
+    default: return run_svd<__nv_bfloat16>(p, ldw, ws, tol, max_sweeps, sweeps_out_host, st, ptrs.data());
   }
 }
 
