@@ -149,15 +149,18 @@ class Factorisation:
         return A, B
 
 
-def suggest_batch(m: int, n: int, device=None, limit_bytes: int = 16 << 30) -> int:
+def suggest_batch(m: int, n: int, device=None, limit_bytes: int = 32 << 30) -> int:
     """How many same-shape weights to factorise per call: the inner eigen-solve runs one CTA per block pair
     (128 vectors), one wave of them is the cheapest, and the two streaming passes need one wave's worth of pairs to
     occupy every SM.  So: as many matrices as fit pairs * batch <= SM count, bounded by workspace memory."""
     _require_cuda()
     sms = torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device()).multi_processor_count
     pairs = (min(m, n) + 127) // 128
-    per = load().asvd_svd_workspace_bytes(int(m), int(n), 1)
-    return int(max(1, min(sms // max(pairs, 1), limit_bytes // max(per, 1), 32)))
+    lib = load()
+    b = int(max(1, min(sms // max(pairs, 1), 32)))
+    while b > 1 and lib.asvd_svd_workspace_bytes(int(m), int(n), b) > limit_bytes:      # part of the workspace is per call
+        b -= 1
+    return b
 
 
 def scaled_svd(weights: Sequence[torch.Tensor], scales: Optional[Sequence[Optional[torch.Tensor]]] = None,

@@ -80,7 +80,7 @@ unsigned long long launches(int k) { return g_launches[k].load(); }
 // ------------------------------------------------------------------------------------------------ plan
 constexpr int RECOVER_MAX_SPLITS = 16;     // K splits of the tensor-core recovery GEMM (runs of <= 1024 columns)
 constexpr int RECOVER_RUN = 768;
-SvdPlan make_plan(int m, int n, int batch) {
+SvdPlan make_plan(int m, int n, int batch, bool allow_inner) {
   SvdPlan p;
   memset(&p, 0, sizeof(p));
   p.m = m; p.n = n; p.batch = batch;
@@ -134,7 +134,23 @@ SvdPlan make_plan(int m, int n, int batch) {
   // and [b1|b2] of the weight (transposed when the vectors are its columns)
   p.off_As = take(sizeof(__nv_bfloat16) * 3 * (size_t)p.nv_pad * p.len_pad);
   p.off_Bs = take(sizeof(__nv_bfloat16) * 2 * (size_t)p.nv_pad * p.len_pad);
-  p.off_Yp = take(sizeof(float) * RECOVER_MAX_SPLITS * (size_t)p.nv_pad * p.ldy);    // fp32 partial results of the K splits
+  // Gram pre-conditioner (see gram_precondition): shapes at least 2:1 whose short side is worth it and whose long side
+  // the plane GEMM can contract
+  p.gram_pre = (allow_inner && p.len_pad >= 2 * p.nv_pad && p.nv_pad >= 1024 && p.len_pad <= RECOVER_MAX_SPLITS * 1024) ? 1 : 0;
+  {
+    size_t part = (size_t)RECOVER_MAX_SPLITS * p.nv_pad * p.ldy;                     // fp32 partial results of the K splits
+    if (p.gram_pre) {
+      const size_t inner_splits = (size_t)((p.nv_pad + RECOVER_RUN - 1) / RECOVER_RUN);
+      const size_t a = inner_splits * p.nv_pad * p.len_pad, g = (size_t)RECOVER_MAX_SPLITS * p.nv_pad * p.nv_pad;
+      if (a > part) part = a;
+      if (g > part) part = g;
+    }
+    p.off_Yp = take(sizeof(float) * part);
+  }
+  if (p.gram_pre) {
+    p.off_Gm = take(sizeof(float) * (size_t)batch * p.nv_pad * p.nv_pad);
+    p.off_inner = take(make_plan(p.nv, p.nv, batch, false).bytes);
+  }
   p.bytes = off;
   return p;
 }
@@ -1022,10 +1038,11 @@ __global__ void __launch_bounds__(256) split_w_kernel(const T* __restrict__ W, i
   }
 }
 
-// Y = (sum of the K-split partial results, fixed order) * column scale
+// Y = (sum of the K-split partial results, fixed order) * column scale * row scale; columns >= ncols are written as 0
 __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ Yp, int nsplit, int64_t split_stride,
                                                            float* __restrict__ Y, int64_t total, int ldy,
-                                                           const float* __restrict__ cscale, int ncols) {
+                                                           const float* __restrict__ cscale, int ncols,
+                                                           const float* __restrict__ rscale, int nrows) {
   const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (e >= total) return;
   float4 acc = *reinterpret_cast<const float4*>(Yp + e);
@@ -1033,12 +1050,37 @@ __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restri
     const float4 v = *reinterpret_cast<const float4*>(Yp + q * split_stride + e);
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
-  if (cscale) {
-    const int c = (int)(e % ldy);
-    acc.x *= c < ncols ? cscale[c] : 0.f; acc.y *= c + 1 < ncols ? cscale[c + 1] : 0.f;
-    acc.z *= c + 2 < ncols ? cscale[c + 2] : 0.f; acc.w *= c + 3 < ncols ? cscale[c + 3] : 0.f;
+  const int c = (int)(e % ldy), r = (int)(e / ldy);
+  float a[4] = {acc.x, acc.y, acc.z, acc.w};
+  const float rs = rscale ? (r < nrows ? rscale[r] : 0.f) : 1.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (c + k >= ncols) a[k] = 0.f;
+    else a[k] *= (cscale ? cscale[c + k] : 1.f) * rs;
   }
-  *reinterpret_cast<float4*>(Y + e) = acc;
+  *reinterpret_cast<float4*>(Y + e) = make_float4(a[0], a[1], a[2], a[3]);
+}
+
+// row-major [nv_pad, ld] -> block-tiled working layout (inverse of untile_kernel)
+__global__ void __launch_bounds__(256) tile_kernel(const float* __restrict__ Xr, float* __restrict__ Xt, int nv_pad, int ld) {
+  const int vec = blockIdx.y;
+  const int col4 = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (col4 >= ld) return;
+  *reinterpret_cast<float4*>(Xt + xt_off(vec, col4, ld >> 5)) = *reinterpret_cast<const float4*>(Xr + (int64_t)vec * ld + col4);
+}
+
+// planes [a1|a2|a3] of W[i][l] * s[l]^2 (the Gram matrix of the ROWS of W diag(s) contracts W s^2 against W)
+template <typename T>
+__global__ void __launch_bounds__(256) split_ws2_kernel(const T* __restrict__ W, int64_t ldw, int m, int n,
+                                                        const float* __restrict__ s, int len_pad, __nv_bfloat16* __restrict__ As) {
+  const int i = blockIdx.y;
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m || l >= n) return;
+  const float sl = s[l];
+  __nv_bfloat16 a1, a2, a3;
+  bf16_planes3(to_f32<T>(W[(int64_t)i * ldw + l]) * sl * sl, a1, a2, a3);
+  __nv_bfloat16* dst = As + (int64_t)i * (3 * (int64_t)len_pad) + l;
+  dst[0] = a1; dst[len_pad] = a2; dst[2 * (int64_t)len_pad] = a3;
 }
 
 // ------------------------------------------------------------------------------------------------ extract (a5, a6)
@@ -1101,9 +1143,12 @@ static void build_pair_table(const SvdPlan& p, std::vector<int2>& tab) {
   }
 }
 
+constexpr int MODE_SKIP_PREP = 1;          // X already holds the vectors (block-tiled)
+constexpr int MODE_STOP_AT_VECTORS = 2;    // return once Xr holds the unit vectors (no recovery, no sort)
+
 template <typename T>
 static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, int max_sweeps, int* sweeps_out,
-                   cudaStream_t st, const void* const* h_W) {
+                   cudaStream_t st, const void* const* h_W, int mode = 0, float conv_tol = 0.f) {
   const void* const* d_W = reinterpret_cast<const void* const*>(ws + p.off_ptrs);
   const int2* d_pairs = reinterpret_cast<const int2*>(ws + p.off_pairs);
   float* X = reinterpret_cast<float*>(ws + p.off_X);
@@ -1131,7 +1176,7 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
     attrs_set = true;
   }
 
-  ASVD_CUDA_CHECK(cudaMemsetAsync(X, 0, sizeof(float) * xs * p.batch, st));
+  if (!(mode & MODE_SKIP_PREP)) ASVD_CUDA_CHECK(cudaMemsetAsync(X, 0, sizeof(float) * xs * p.batch, st));
   ASVD_CUDA_CHECK(cudaMemsetAsync(done, 0, sizeof(int) * p.batch, st));
   ASVD_CUDA_CHECK(cudaMemsetAsync(status, 0, sizeof(int) * p.batch, st));
   {
@@ -1142,7 +1187,7 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
     ASVD_CUDA_CHECK(cudaMemcpyAsync(track, h_track.data(), sizeof(int) * h_track.size(), cudaMemcpyHostToDevice, st));
     ASVD_CUDA_CHECK(cudaStreamSynchronize(st));
   }
-  {
+  if (!(mode & MODE_SKIP_PREP)) {
     // initial order of the vectors: ascending norm (ASVD_B200_PRESORT=0 keeps the given order).  sigma / norm / perm are
     // free until the epilogue; the slot table lives in the (not yet used) Y buffer.
     const char* ps_env = getenv("ASVD_B200_PRESORT");
@@ -1184,12 +1229,15 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
   }
   const char* pre_env = getenv("ASVD_B200_TOL_PRE");   // default 5 tol = 2e-5: `tol` itself sits on the fp32 plateau, where passing is a coin flip
   float tol_pre = pre_env ? (float)atof(pre_env) : 5.f * tol;
+  if (conv_tol > 0.f) tol_pre = conv_tol;          // pre-conditioning stage: stop early, the main sweeps finish the job
   if (tol_pre < tol) tol_pre = tol;
   std::vector<unsigned> h_maxoff(2 * (size_t)p.batch);
   std::vector<int> h_done(p.batch, 0), h_sweeps(p.batch, 0);
   int sweep = 0;
   bool all_done = false;
-  bool near_seen = false;      // some pair of a running matrix was already (nearly) orthogonal in an earlier sweep
+  // some pair of a running matrix was already (nearly) orthogonal in an earlier sweep -- or the vectors arrive
+  // pre-conditioned, where the single-pass Gram could not see the cosines that are left
+  bool near_seen = (mode & MODE_SKIP_PREP) != 0;
   for (; sweep < max_sweeps && !all_done; ++sweep) {
     // single-pass TF32 Gram only while every pair still needs work; afterwards the 3-term split (fp32-accurate),
     // without which the threshold test could not skip converged pairs nor certify convergence
@@ -1251,6 +1299,12 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
   ASVD_LAUNCH(K_FINAL, st, (untile_kernel<<<dim3((p.len_pad / 4 + 255) / 256, p.nv_pad, p.batch), 256, 0, st>>>(X, Xr, xs, p.nv_pad, p.len_pad)));
   ASVD_LAUNCH(K_FINAL, st, (rownorm_kernel<<<dim3(p.nv_pad, p.batch), 256, 0, st>>>(Xr, xs, p.len_pad, p.len_pad, 1, sigma, p.nv_pad, status, nullptr)));
   ASVD_CUDA_CHECK(cudaGetLastError());
+  if (mode & MODE_STOP_AT_VECTORS) {
+    ASVD_CUDA_CHECK(cudaStreamSynchronize(st));
+    prof_collect();
+    if (sweeps_out) for (int b = 0; b < p.batch; ++b) sweeps_out[b] = h_sweeps[b];
+    return ASVD_OK;
+  }
   {
     GemmBatch gb;
     memset(&gb, 0, sizeof(gb));
@@ -1293,7 +1347,7 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
                                    p.len_pad, k0, (p.len_pad - k0 < run) ? p.len_pad - k0 : run, nullptr, st);
         if (rc == 0)
           sum_partials_kernel<<<(unsigned)((ystride / 4 + 255) / 256), 256, 0, st>>>(Yp, used, ystride, Y + b * gb.strideC, ystride,
-                                                                                 p.ldy, p.tall ? sb : nullptr, p.nv);
+                                                                                 p.ldy, p.tall ? sb : nullptr, p.nv, nullptr, 0);
         prof_end(K_FINAL, st);
         if (rc < 0) { set_error("recovery GEMM launch failed (%d)", rc); return ASVD_ERR_CUDA; }
         if (rc == 0) continue;
@@ -1325,6 +1379,109 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
   for (int b = 0; b < p.batch; ++b)
     if (h_status[b]) { set_error("non-finite values in weight %d of the batch (or its scale)", b); return ASVD_ERR_NONFINITE; }
   if (!all_done) { set_error("sweep limit %d reached above tolerance %g", max_sweeps, (double)tol); return ASVD_ERR_NOT_CONVERGED; }
+  return ASVD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ Gram pre-conditioner
+// Rectangular weights (long vectors, few of them): every round of the sweeps streams vectors 2.7x longer than there
+// are of them although the rotations only depend on their nv x nv Gram matrix.  So:
+//   1. G = X X^T exactly (bf16 plane GEMM from the original weight: b_i b_j products, scale applied in fp32);
+//   2. the same block-Jacobi machinery on G itself, an nv x nv problem: its unit vectors are the eigenvectors Q of G,
+//      i.e. the rotation the long problem is looking for, to the accuracy the squared conditioning allows;
+//   3. X1 = Q^T X, again as an exact plane GEMM from the ORIGINAL weight (nothing of step 2's error survives except
+//      through Q being slightly off), written in the working layout;
+//   4. the ordinary sweeps on X1 finish the job -- typically one sweep with a few rotations and the verification --
+//      under the ordinary convergence test, so the result has the accuracy of the direct path.
+// (the Gram shortcut is acceptable as a pre-conditioner only.)
+template <typename T>
+static int gram_precondition(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, int max_sweeps, cudaStream_t st,
+                             const void* const* h_W, int* inner_sweeps) {
+  const SvdPlan pi = make_plan(p.nv, p.nv, p.batch, false);
+  unsigned char* wi = ws + p.off_inner;
+  float* Gm = reinterpret_cast<float*>(ws + p.off_Gm);
+  float* X = reinterpret_cast<float*>(ws + p.off_X);
+  float* Xr = reinterpret_cast<float*>(ws + p.off_Xr);
+  float* scale = reinterpret_cast<float*>(ws + p.off_scale);
+  float* Yp = reinterpret_cast<float*>(ws + p.off_Yp);
+  __nv_bfloat16* As = reinterpret_cast<__nv_bfloat16*>(ws + p.off_As);
+  __nv_bfloat16* Bs = reinterpret_cast<__nv_bfloat16*>(ws + p.off_Bs);
+  const int64_t gs = (int64_t)p.nv_pad * p.nv_pad, xs = (int64_t)p.nv_pad * p.len_pad;
+  const int b_planes = std::is_same<T, __nv_bfloat16>::value ? 1 : 2;
+  auto runs = [](int K) {
+    int ns = (K + RECOVER_RUN - 1) / RECOVER_RUN;
+    if (ns > RECOVER_MAX_SPLITS) ns = RECOVER_MAX_SPLITS;
+    return (int)round_up((K + ns - 1) / ns, 64);
+  };
+  // ---- 1. Gram matrices
+  for (int b = 0; b < p.batch; ++b) {
+    const T* W = reinterpret_cast<const T*>(h_W[b]);
+    const float* sb = scale + (int64_t)b * p.n;
+    prof_begin(K_PREP, st);
+    ASVD_CUDA_CHECK(cudaMemsetAsync(Bs, 0, sizeof(__nv_bfloat16) * 2 * (size_t)p.nv_pad * p.len_pad, st));
+    split_w_kernel<T><<<dim3((p.n + 31) / 32, (p.m + 31) / 32), 256, 0, st>>>(W, ldw, p.m, p.n, p.tall, p.len_pad, Bs);
+    const __nv_bfloat16* A = Bs;
+    int a_planes = b_planes;
+    int64_t lda = 2 * (int64_t)p.len_pad;
+    if (!p.tall) {
+      ASVD_CUDA_CHECK(cudaMemsetAsync(As, 0, sizeof(__nv_bfloat16) * 3 * (size_t)p.nv_pad * p.len_pad, st));
+      split_ws2_kernel<T><<<dim3((p.n + 255) / 256, p.m), 256, 0, st>>>(W, ldw, p.m, p.n, sb, p.len_pad, As);
+      A = As; a_planes = 3; lda = 3 * (int64_t)p.len_pad;
+    }
+    const int run = runs(p.len_pad);
+    int rc = 0, used = 0;
+    for (int k0 = 0; k0 < p.len_pad && rc == 0; k0 += run, ++used)
+      rc = tc::gemm_planes_f32(A, lda, a_planes, Bs, 2 * (int64_t)p.len_pad, b_planes, Yp + used * gs, p.nv_pad, p.nv_pad, p.nv,
+                               p.len_pad, k0, (p.len_pad - k0 < run) ? p.len_pad - k0 : run, nullptr, st);
+    if (rc != 0) { prof_end(K_PREP, st); set_error("Gram GEMM launch failed (%d)", rc); return ASVD_ERR_CUDA; }
+    sum_partials_kernel<<<(unsigned)((gs / 4 + 255) / 256), 256, 0, st>>>(Yp, used, gs, Gm + b * gs, gs, p.nv_pad,
+                                                                      p.tall ? sb : nullptr, p.nv, p.tall ? sb : nullptr, p.nv);
+    prof_end(K_PREP, st);
+  }
+  ASVD_CUDA_CHECK(cudaGetLastError());
+  // ---- 2. the square problem on G
+  {
+    std::vector<const void*> gp(2 * (size_t)p.batch, nullptr);
+    for (int b = 0; b < p.batch; ++b) gp[b] = Gm + b * gs;
+    ASVD_CUDA_CHECK(cudaMemcpyAsync(wi + pi.off_ptrs, gp.data(), sizeof(void*) * 2 * p.batch, cudaMemcpyHostToDevice, st));
+    std::vector<int2> tab;
+    build_pair_table(pi, tab);
+    if (!tab.empty())
+      ASVD_CUDA_CHECK(cudaMemcpyAsync(wi + pi.off_pairs, tab.data(), sizeof(int2) * tab.size(), cudaMemcpyHostToDevice, st));
+    float* iscale = reinterpret_cast<float*>(wi + pi.off_scale);
+    const int64_t ne = (int64_t)p.batch * pi.n;
+    fill_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(iscale, 1.f, ne);
+    ASVD_CUDA_CHECK(cudaStreamSynchronize(st));
+    const char* it_env = getenv("ASVD_B200_INNER_TOL");
+    // the square stage only has to hand over vectors orthogonal to ~1e-3: the main sweeps converge quadratically from
+    // there (measured 11008x4096 / 4096x11008, ms per batch of four: 282 / 349 at full tolerance, 273 / 343 at 1e-3, 285 / 346 at 1e-2)
+    const float inner_tol = it_env ? (float)atof(it_env) : 1e-3f;
+    const int rc = run_svd<float>(pi, p.nv_pad, wi, tol, max_sweeps, inner_sweeps, st, gp.data(), MODE_STOP_AT_VECTORS, inner_tol);
+    if (rc != ASVD_OK) return rc;          // CUDA errors only: this mode never reports non-convergence
+  }
+  // ---- 3. X1 = Q^T X from the original weight, into the working layout
+  const float* Q = reinterpret_cast<const float*>(wi + pi.off_Xr);
+  const int64_t qs = (int64_t)pi.nv_pad * pi.len_pad;
+  for (int b = 0; b < p.batch; ++b) {
+    const T* W = reinterpret_cast<const T*>(h_W[b]);
+    const float* sb = scale + (int64_t)b * p.n;
+    prof_begin(K_PREP, st);
+    ASVD_CUDA_CHECK(cudaMemsetAsync(Bs, 0, sizeof(__nv_bfloat16) * 2 * (size_t)p.nv_pad * p.len_pad, st));
+    // rows = positions along the long dimension, contraction along the short one
+    split_w_kernel<T><<<dim3((p.n + 31) / 32, (p.m + 31) / 32), 256, 0, st>>>(W, ldw, p.m, p.n, p.tall ? 0 : 1, pi.len_pad, Bs);
+    split_x_kernel<<<dim3((pi.len_pad / 4 + 255) / 256, pi.nv_pad), 256, 0, st>>>(Q + b * qs, p.tall ? sb : nullptr, pi.nv_pad,
+                                                                               pi.len_pad, p.nv, As);
+    const int run = runs(pi.len_pad);
+    int rc = 0, used = 0;
+    for (int k0 = 0; k0 < pi.len_pad && rc == 0; k0 += run, ++used)
+      rc = tc::gemm_planes_f32(As, 3 * (int64_t)pi.len_pad, 3, Bs, 2 * (int64_t)pi.len_pad, b_planes, Yp + used * xs, p.len_pad,
+                               p.nv_pad, p.len, pi.len_pad, k0, (pi.len_pad - k0 < run) ? pi.len_pad - k0 : run, nullptr, st);
+    if (rc != 0) { prof_end(K_PREP, st); set_error("pre-conditioning GEMM launch failed (%d)", rc); return ASVD_ERR_CUDA; }
+    sum_partials_kernel<<<(unsigned)((xs / 4 + 255) / 256), 256, 0, st>>>(Yp, used, xs, Xr + b * xs, xs, p.len_pad,
+                                                                      p.tall ? nullptr : sb, p.len, nullptr, 0);
+    tile_kernel<<<dim3((p.len_pad / 4 + 255) / 256, p.nv_pad), 256, 0, st>>>(Xr + b * xs, X + b * xs, p.nv_pad, p.len_pad);
+    prof_end(K_PREP, st);
+  }
+  ASVD_CUDA_CHECK(cudaGetLastError());
   return ASVD_OK;
 }
 
@@ -1428,11 +1585,28 @@ int asvd_scaled_svd(const void* const* W_host_ptrs, int w_dtype, int64_t ldw, in
   ASVD_CUDA_CHECK(cudaGetLastError());
   // the pageable host buffers above must outlive the async copies
   ASVD_CUDA_CHECK(cudaStreamSynchronize(st));
-  switch (w_dtype) {
-    case ASVD_F32: return run_svd<float>(p, ldw, ws, tol, max_sweeps, sweeps_out_host, st, ptrs.data());
-    case ASVD_F16: return run_svd<__half>(p, ldw, ws, tol, max_sweeps, sweeps_out_host, st, ptrs.data());
-    default: return run_svd<__nv_bfloat16>(p, ldw, ws, tol, max_sweeps, sweeps_out_host, st, ptrs.data());
+  // ASVD_B200_GRAMPRE=0 switches the Gram pre-conditioner of the rectangular shapes off (A/B runs)
+  const char* gp_env = getenv("ASVD_B200_GRAMPRE");
+  const char* simt_env = getenv("ASVD_B200_SIMT");
+  const bool gram_pre = p.gram_pre && w_dtype != ASVD_F32 && !(gp_env && gp_env[0] == '0') && !(simt_env && simt_env[0] == '1');
+  int mode = 0;
+  std::vector<int> inner_sweeps(batch, 0);
+  if (gram_pre) {
+    const int rc = (w_dtype == ASVD_F16)
+                       ? gram_precondition<__half>(p, ldw, ws, tol, max_sweeps, st, ptrs.data(), inner_sweeps.data())
+                       : gram_precondition<__nv_bfloat16>(p, ldw, ws, tol, max_sweeps, st, ptrs.data(), inner_sweeps.data());
+    if (rc != ASVD_OK) return rc;
+    mode = MODE_SKIP_PREP;
   }
+  int rc;
+  switch (w_dtype) {
+    case ASVD_F32: rc = run_svd<float>(p, ldw, ws, tol, max_sweeps, sweeps_out_host, st, ptrs.data(), mode); break;
+    case ASVD_F16: rc = run_svd<__half>(p, ldw, ws, tol, max_sweeps, sweeps_out_host, st, ptrs.data(), mode); break;
+    default: rc = run_svd<__nv_bfloat16>(p, ldw, ws, tol, max_sweeps, sweeps_out_host, st, ptrs.data(), mode); break;
+  }
+  if (gram_pre && sweeps_out_host)          // report the sweeps of both stages
+    for (int b = 0; b < batch; ++b) sweeps_out_host[b] += inner_sweeps[b];
+  return rc;
 }
 
 int asvd_svd_sigma(const void* workspace, int m, int n, int batch, int b, float* sigma_out, void* stream) {
