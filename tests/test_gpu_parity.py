@@ -374,3 +374,36 @@ def test_suggest_batch_fills_one_wave():
         b = L.suggest_batch(m, n)
         pairs = (min(m, n) + 127) // 128
         assert 1 <= b <= 32 and b * pairs <= max(sms, pairs)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_gram_preconditioned_rectangles(dtype, monkeypatch):
+    """Shapes that take the Gram pre-conditioner (>= 2:1, >= 1024 vectors, 16-bit weights), both orientations: same
+    contract as every other shape, and the same singular values as the direct path (ASVD_B200_GRAMPRE=0)."""
+    L = _lib()
+    for (m, n) in [(2304, 1024), (1024, 2304)]:
+        W, s = O.synthetic_weight(m, n, seed=31)
+        W = W.to(dtype)
+        scale = (s ** 0.5 + 1e-6).float()
+        fact, rel, rec = check_factorisation(W, scale, 0.9, "UV")
+        monkeypatch.setenv("ASVD_B200_GRAMPRE", "0")
+        direct = L.scaled_svd([W.cuda()], [scale.cuda()])
+        monkeypatch.delenv("ASVD_B200_GRAMPRE")
+        s1, s2 = fact.sigma().double(), direct.sigma().double()
+        assert ((s1 - s2).abs() / (s2 + 1e-3 * s2[0])).max().item() < 2e-5
+
+
+def test_recovery_tensor_core_matches_simt(monkeypatch):
+    """The bf16-plane recovery GEMM against the fp32 SIMT GEMM it replaces: sigma and factors."""
+    L = _lib()
+    W, s = O.synthetic_weight(1280, 1024, seed=41)
+    scale = (s ** 0.5 + 1e-6).float().cuda()
+    a = L.scaled_svd([W.cuda()], [scale])
+    monkeypatch.setenv("ASVD_B200_RECOVER", "simt")
+    b = L.scaled_svd([W.cuda()], [scale])
+    monkeypatch.delenv("ASVD_B200_RECOVER")
+    s1, s2 = a.sigma().double(), b.sigma().double()
+    assert ((s1 - s2).abs() / (s2 + 1e-3 * s2[0])).max().item() < 1e-5
+    A1, B1 = a.extract(460, "UV", torch.float32)
+    A2, B2 = b.extract(460, "UV", torch.float32)
+    assert ((A1 @ B1 - A2 @ B2) * scale).norm().item() / ((A2 @ B2) * scale).norm().item() < 1e-4
