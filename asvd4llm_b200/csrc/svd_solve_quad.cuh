@@ -53,6 +53,7 @@ __device__ __forceinline__ float3 quad_rotation(float gpp, float gqq, float gpq,
   if (gpq * gpq > 1e-16f * (gpp * gqq) && gpq != 0.f) {         // |cos| > 1e-8
     const float s = sqrt_ftz(fmaf(delta, delta, h * h));
     t = copysignf(fabsf(h) * rcp_ftz(fabsf(delta) + s), delta * h);
+    t = (fabsf(t) <= 1.f) ? t : 0.f;          // |t| <= 1 by construction; anything else is underflow debris (inf / NaN): no rotation
     c = rsqrt_ftz(fmaf(t, t, 1.f));
   }
   return make_float3(-t * rho, t * rho_inv, c);
