@@ -1172,6 +1172,7 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
   if (!attrs_set) {
     ASVD_CUDA_CHECK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
     ASVD_CUDA_CHECK(cudaFuncSetAttribute(solve_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVEQ_SMEM));
+    ASVD_CUDA_CHECK(upload_quad_schedule());
     ASVD_CUDA_CHECK(cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPDATE_SMEM));
     ASVD_CUDA_CHECK(cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 16384));
     attrs_set = true;

@@ -9,8 +9,8 @@
 //   * the 2x2 pivot blocks lie in the diagonal patches: the 16 diagonal-patch threads compute the rotation
 //     parameters straight from their registers (no publish step, no second barrier);
 //   * a step is: parameters -> one 256-thread barrier -> 128 FMAs per thread, with no data movement at all;
-//   * data moves only once per ROUND (4 steps): the circle method over the 32 quads, (0,L) fixed, the others
-//     advancing one slot along T1..T15,B15..B0, moves whole quads between neighbouring patches through shared memory.
+//   * data moves only once per ROUND (4 steps): a recursive tournament over the 32 quads (c_quad_src) moves whole quads
+//     between patches through shared memory, at most half of them per move.
 // Schedule: 3 steps inside the quads ((0,1)(2,3) / (0,2)(1,3) / (0,3)(1,2)), then 31 rounds of 4 steps pairing
 // L_i with H_(i+j)%4, j = 0..3: 127 steps, every pair of positions exactly once.
 // The accumulated rotation R is kept by the other 256 threads as 8x8 patches too (column operations only).  They do
@@ -23,7 +23,7 @@ constexpr int QSTEPS = 127;
 constexpr int QROUNDS = 31;
 constexpr int QFOLDS = 3;                      // after rounds 7, 15, 23
 constexpr size_t SOLVEQ_SMEM = sizeof(float) * (2 * JK * SLD) + sizeof(float2) * QSTEPS * 64 + sizeof(float) * 64 +
-                               sizeof(int) * JK + sizeof(float) * JK * (3 + QFOLDS) + sizeof(uint64_t) * (QSTEPS + 1);
+                               sizeof(int) * JK + sizeof(float) * JK * (3 + QFOLDS) + sizeof(uint64_t) * (QSTEPS + 1) + (QROUNDS - 1) * 32;
 
 // local positions (p, q) of pair k in a step of the given type: 0-2 inside the quads, 3-6 = L_i with H_(i+type-3)%4
 __host__ __device__ constexpr int qp_p(int type, int k) { return type == 0 ? 2 * k : type <= 2 ? (k < 2 ? k : k + 2) : k; }
@@ -162,34 +162,93 @@ __device__ __forceinline__ void quad_r_step(float (&r)[8][8], const float2* cs_s
 // row-wise accesses (chunk = pc) and the transposed ones (chunk = pa) fall on distinct banks; and the 16 diagonal
 // patches sit in lanes 0-15 of ONE warp, the only one that runs the rotation-parameter code.
 __device__ __forceinline__ float* quad_stage(float* st, int pos, int chunk) { return st + pos * JK + (chunk << 2); }
-// source slot (first position of the quad) whose contents move into quad (g, h) at the end of a round
-__device__ __forceinline__ int quad_src(int g, int h) {
-  if (h == 0) return g <= 1 ? (g == 0 ? 0 : 4) : 8 * (g - 1);
-  return g == 15 ? 8 * 15 : 8 * (g + 1) + 4;
+// Schedule of the quad moves: c_quad_src[r][2g + h] = first position of the quad whose contents move into slot (g, h)
+// after round r.  A recursive tournament over the 32 quads: 16 rounds in which slot L of group g meets the H quads of
+// all 16 groups (only the H quads move, one group along), then the L quads of groups 8-15 drop into the H slots of
+// groups 0-7 (and the H quads of groups 0-7 into the L slots of 8-15) and both halves repeat the scheme with 8 groups,
+// then 4, 2, 1: 16 + 8 + 4 + 2 + 1 = 31 rounds, every pair of quads exactly once (checked on the host when the table
+// is built), and in every move at least half of the quads stay where they are -- the staging traffic of a move is
+// the dominant cost of the sweep after the dependent chain, and a sub-block whose row quad and column quad both stay
+// never goes through shared memory.
+__constant__ unsigned char c_quad_src[(QROUNDS - 1) * 32];
+
+static bool build_quad_schedule(unsigned char* tab /* [(QROUNDS-1)*32] */) {
+  int cur[32];                                   // quad id at slot 2g + h
+  for (int i = 0; i < 32; ++i) cur[i] = i;
+  bool met[32][32] = {};
+  int round = 0;
+  for (int B = 16; B >= 1; B >>= 1) {
+    for (int k = 0; k < B; ++k, ++round) {
+      for (int g = 0; g < 16; ++g) {
+        const int a = cur[2 * g], b = cur[2 * g + 1];
+        if (met[a][b]) return false;
+        met[a][b] = met[b][a] = true;
+      }
+      if (round == QROUNDS - 1) break;
+      int src[32];                               // slot -> slot its new content comes from
+      for (int i = 0; i < 32; ++i) src[i] = i;
+      if (k < B - 1) {                           // shift the H quads one group along inside every block of B groups
+        for (int g = 0; g < 16; ++g) {
+          const int b0 = g - g % B;
+          src[2 * g + 1] = 2 * (b0 + (g - b0 + 1) % B) + 1;
+        }
+      } else {                                   // next level: first half of each block takes the L quads, second the H quads
+        const int h = B / 2;
+        for (int b0 = 0; b0 < 16; b0 += B)
+          for (int i = 0; i < h; ++i) {
+            src[2 * (b0 + i) + 1] = 2 * (b0 + h + i);          // L of the second half -> H slot of the first half
+            src[2 * (b0 + h + i)] = 2 * (b0 + i) + 1;          // H of the first half  -> L slot of the second half
+          }
+      }
+      int nxt[32];
+      for (int i = 0; i < 32; ++i) { nxt[i] = cur[src[i]]; tab[round * 32 + i] = (unsigned char)(8 * (src[i] >> 1) + 4 * (src[i] & 1)); }
+      for (int i = 0; i < 32; ++i) cur[i] = nxt[i];
+    }
+  }
+  if (round != QROUNDS - 1) return false;
+  for (int a = 0; a < 32; ++a)
+    for (int b = 0; b < 32; ++b)
+      if (a != b && !met[a][b]) return false;
+  return true;
+}
+static cudaError_t upload_quad_schedule() {
+  static bool done = false;
+  if (done) return cudaSuccess;
+  unsigned char tab[(QROUNDS - 1) * 32];
+  if (!build_quad_schedule(tab)) return cudaErrorUnknown;
+  cudaError_t e = cudaMemcpyToSymbol(c_quad_src, tab, sizeof(tab));
+  if (e == cudaSuccess) done = true;
+  return e;
 }
 
 // staging chunk of the column quad that starts at position `pos`
 __device__ __forceinline__ int quad_chunk(int pos) { return ((pos >> 2) & 1) * 16 + (pos >> 3); }
 
-// every thread writes its patch (row 8pa+i, column-quad chunks pc and 16+pc) ...
-__device__ __forceinline__ void quad_stage_write(float* st, const float (&g)[8][8], int pa, int pc) {
+// Every thread writes the sub-blocks of its patch that leave it (row 8pa+i, column-quad chunks pc and 16+pc) ...
+// mv[2 hr + hc]: the sub-block (row quad hr, column quad hc) changes its content in this move
+__device__ __forceinline__ void quad_stage_write(float* st, const float (&g)[8][8], int pa, int pc, const bool (&mv)[4]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    *reinterpret_cast<float4*>(quad_stage(st, 8 * pa + i, pc)) = make_float4(g[i][0], g[i][1], g[i][2], g[i][3]);
-    *reinterpret_cast<float4*>(quad_stage(st, 8 * pa + i, 16 + pc)) = make_float4(g[i][4], g[i][5], g[i][6], g[i][7]);
+    if (mv[2 * (i >> 2)]) *reinterpret_cast<float4*>(quad_stage(st, 8 * pa + i, pc)) = make_float4(g[i][0], g[i][1], g[i][2], g[i][3]);
+    if (mv[2 * (i >> 2) + 1])
+      *reinterpret_cast<float4*>(quad_stage(st, 8 * pa + i, 16 + pc)) = make_float4(g[i][4], g[i][5], g[i][6], g[i][7]);
   }
 }
-// ... and reads the patch its slot holds after the move: rows from the source row quads (rL, rH: first positions; pass
-// 8pa and 8pa+4 when the rows stay), columns from the source column quads
-__device__ __forceinline__ void quad_stage_read(float* st, float (&g)[8][8], int rL, int rH, int cL, int cH) {
+// ... and reads the sub-blocks its slot receives: rows from the source row quads (rL, rH: first positions; 8pa and
+// 8pa+4 when the rows stay), columns from the source column quads
+__device__ __forceinline__ void quad_stage_read(float* st, float (&g)[8][8], int rL, int rH, int cL, int cH, const bool (&mv)[4]) {
   const int kL = quad_chunk(cL), kH = quad_chunk(cH);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int sp = (i < 4 ? rL : rH) + (i & 3);
-    const float4 lo = *reinterpret_cast<const float4*>(quad_stage(st, sp, kL));
-    const float4 hi = *reinterpret_cast<const float4*>(quad_stage(st, sp, kH));
-    g[i][0] = lo.x; g[i][1] = lo.y; g[i][2] = lo.z; g[i][3] = lo.w;
-    g[i][4] = hi.x; g[i][5] = hi.y; g[i][6] = hi.z; g[i][7] = hi.w;
+    if (mv[2 * (i >> 2)]) {
+      const float4 lo = *reinterpret_cast<const float4*>(quad_stage(st, sp, kL));
+      g[i][0] = lo.x; g[i][1] = lo.y; g[i][2] = lo.z; g[i][3] = lo.w;
+    }
+    if (mv[2 * (i >> 2) + 1]) {
+      const float4 hi = *reinterpret_cast<const float4*>(quad_stage(st, sp, kH));
+      g[i][4] = hi.x; g[i][5] = hi.y; g[i][6] = hi.z; g[i][7] = hi.w;
+    }
   }
 }
 
@@ -209,6 +268,7 @@ solve_quad_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat
   float* dfin = dmov + JK;                                  // [JK] final scales
   float* dhist = dfin + JK;                                 // [QFOLDS][JK] scales folded into G (and, later, into R)
   uint64_t* mb = reinterpret_cast<uint64_t*>(dhist + QFOLDS * JK);   // [QSTEPS + 1] one-shot "step published" barriers
+  unsigned char* qsrc = reinterpret_cast<unsigned char*>(mb + QSTEPS + 1);   // [(QROUNDS-1)*32] copy of c_quad_src (lanes index it divergently)
 
   const int b = blockIdx.y, p = blockIdx.x;
   if (done[b]) return;
@@ -221,6 +281,7 @@ solve_quad_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat
     return;
   }
   if (tid < QSTEPS + 1) tc::mbar_init(&mb[tid], 1);         // ordered before their first use by the prologue's barriers
+  for (int i = tid; i < (QROUNDS - 1) * 32; i += SOLVE_THREADS) qsrc[i] = c_quad_src[i];
   if (!solve_prologue(Gpart, chunks, idx, b, pr, tid, G, red, pairflag, maxoff_bits, status, tol, trk, nb, round_stamp,
                       precise, gridDim.y, half_gram))
     return;
@@ -251,8 +312,6 @@ solve_quad_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat
     for (int i = 0; i < 8; ++i) d[i] = 1.f;
     const bool is_diag = (pa == pc);
     const bool lead = lt < 32;
-    const int rsrcL = quad_src(pa, 0), rsrcH = quad_src(pa, 1);
-    const int csrcL = quad_src(pc, 0), csrcH = quad_src(pc, 1);
     auto bar_g = [] { asm volatile("bar.sync 2, 256;" ::: "memory"); };
     bar_g();                                                 // every patch is in registers: G becomes the staging area
 
@@ -283,14 +342,18 @@ solve_quad_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat
 #pragma unroll
           for (int j = 0; j < 8; ++j) g[i][j] *= dr[i] * dc[j];
       }
-      // ---- quad move: one pass through shared memory (rows and columns at once)
-      quad_stage_write(G, g, pa, pc);
+      // ---- quad move: one pass through shared memory (rows and columns at once), only what changes place
+      const unsigned char* qs = qsrc + r * 32;
+      const int rsrcL = qs[2 * pa], rsrcH = qs[2 * pa + 1], csrcL = qs[2 * pc], csrcH = qs[2 * pc + 1];
+      const bool mrL = rsrcL != 8 * pa, mrH = rsrcH != 8 * pa + 4, mcL = csrcL != 8 * pc, mcH = csrcH != 8 * pc + 4;
+      const bool mv[4] = {mrL || mcL, mrL || mcH, mrH || mcL, mrH || mcH};
+      quad_stage_write(G, g, pa, pc, mv);
       if (is_diag) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) dmov[8 * pa + i] = d[i];
       }
       bar_g();
-      quad_stage_read(G, g, rsrcL, rsrcH, csrcL, csrcH);
+      quad_stage_read(G, g, rsrcL, rsrcH, csrcL, csrcH, mv);
       if (is_diag) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) d[i] = dmov[(i < 4 ? rsrcL : rsrcH) + (i & 3)];
@@ -321,7 +384,6 @@ solve_quad_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) r[i][j] = (pa == pc && i == j) ? 1.f : 0.f;
-    const int csrcL = quad_src(pc, 0), csrcH = quad_src(pc, 1);
     auto bar_r = [] { asm volatile("bar.sync 3, 256;" ::: "memory"); };
     quad_r_step<0>(r, csh + 0 * 64, pc, mb, 0);
     quad_r_step<1>(r, csh + 1 * 64, pc, mb, 1);
@@ -345,9 +407,13 @@ solve_quad_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat
           for (int i = 0; i < 8; ++i) r[i][j] *= dc;
         }
       }
-      quad_stage_write(Rs, r, pa, pc);
+      const unsigned char* qs = qsrc + rd * 32;
+      const int csrcL = qs[2 * pc], csrcH = qs[2 * pc + 1];
+      const bool mcL = csrcL != 8 * pc, mcH = csrcH != 8 * pc + 4;
+      const bool mv[4] = {mcL, mcH, mcL, mcH};              // rows never move: only the column quads decide
+      quad_stage_write(Rs, r, pa, pc, mv);
       bar_r();
-      quad_stage_read(Rs, r, 8 * pa, 8 * pa + 4, csrcL, csrcH);
+      quad_stage_read(Rs, r, 8 * pa, 8 * pa + 4, csrcL, csrcH, mv);
       bar_r();
     }
     tc::mbar_wait(&mb[QSTEPS], 0);
