@@ -249,6 +249,31 @@ constexpr int UP_SMEM = UP_BAR_OFFSET + 256 + 1024;
 constexpr int UP_THREADS = 384;
 constexpr uint32_t UP_TMEM_A_HI = 256, UP_TMEM_A_LO = 384;   // column offsets; D buffers at 0 and 64
 
+__device__ __forceinline__ void update_gather_rt(const float* __restrict__ Rp, uint32_t tmem_base, int q, int lane, int half,
+                                                 uint64_t* a_ready) {
+  const int j = q * 32 + lane;
+  const float* src = Rp + j;
+#pragma unroll 1
+  for (int c = 2 * half; c < 2 * half + 2; ++c) {
+    float x[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) x[e] = src[(c * 32 + e) * JK];
+    uint32_t h[32], l[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      const float hh = rna_tf32(x[e]);
+      h[e] = __float_as_uint(hh);
+      l[e] = __float_as_uint(x[e] - hh);
+    }
+    tmem_st_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + UP_TMEM_A_HI + c * 32, h);
+    tmem_st_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + UP_TMEM_A_LO + c * 32, l);
+  }
+  tmem_st_wait();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(a_ready);
+}
+
 __global__ void __launch_bounds__(UP_THREADS, 1)
 update_tc_kernel(const __grid_constant__ CUtensorMap tmX, float* __restrict__ X, int64_t mat_stride, int ldx,
                  const int2* __restrict__ pairs, int pairs_per_mat, int nv_pad, int tiles_total, int tiles_per_cta,
@@ -279,7 +304,7 @@ update_tc_kernel(const __grid_constant__ CUtensorMap tmX, float* __restrict__ X,
     for (int i = 0; i < UP_NH; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < UP_NL; ++i) { mbar_init(&lo_ready[i], 4); mbar_init(&lo_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
-    mbar_init(a_ready, 4);
+    mbar_init(a_ready, 8);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr, 512);
@@ -347,28 +372,10 @@ update_tc_kernel(const __grid_constant__ CUtensorMap tmX, float* __restrict__ X,
   } else if (warp >= 4 && warp < 8) {
     const int q = warp - 4;
     const int j = q * 32 + lane;                           // output vector of this thread = TMEM lane
-    {   // A = R^T: thread j gathers column j of R (coalesced across the warp) -> hi/lo -> tensor memory
-      const float* src = R + (int64_t)idx * (JK * JK) + j;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        float x[32];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) x[e] = src[(c * 32 + e) * JK];
-        uint32_t h[32], l[32];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float hh = rna_tf32(x[e]);
-          h[e] = __float_as_uint(hh);
-          l[e] = __float_as_uint(x[e] - hh);
-        }
-        tmem_st_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + UP_TMEM_A_HI + c * 32, h);
-        tmem_st_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + UP_TMEM_A_LO + c * 32, l);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a_ready);
-    }
+    // A = R^T: thread j gathers column j of R (coalesced across the warp) -> hi/lo -> tensor memory.  The four split
+    // warps take the upper half of the columns (same TMEM lane quadrants), so the gather's L2 latency is paid twice,
+    // not four times, before the first MMA.
+    update_gather_rt(R + (int64_t)idx * (JK * JK), tmem_base, q, lane, 0, a_ready);
     // D tile -> the tile's own landing slot, in the layout the TMA wrote it (rows of 128 B, 32-byte chunks XOR row&3)
     // -> TMA store over the same rows of X.  The slot returns to the producer once the store has read it.
     const int row_off = j * 128;
@@ -422,6 +429,7 @@ update_tc_kernel(const __grid_constant__ CUtensorMap tmX, float* __restrict__ X,
       if (pending_stage >= 0) mbar_arrive(&empty[pending_stage]);
     }
   } else if (warp >= 8) {
+    update_gather_rt(R + (int64_t)idx * (JK * JK), tmem_base, warp - 8, lane, 1, a_ready);
     const int t128 = threadIdx.x - 256;
     int stage = 0; uint32_t phase = 0;
     int ls = 0; uint32_t lph = 0;
