@@ -147,8 +147,8 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # NCCL writes its version banner (and anything NCCL_DEBUG asks for) to stdout; rank 0 prints ONE JSON line there
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug.%h.%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
     from asvd4llm_b200 import _lib
@@ -180,6 +180,20 @@ def main():
     for i in range(args.warmup):
         fact, _ = device_step(i)
     barrier()
+    # A freshly booted box has been seen to take one step 40-80 % longer than its neighbours about a second into the load
+    # (sw_power_cap flagged, clocks back at maximum right after): keep warming up, untimed, until two consecutive steps
+    # agree to 5 % (at most 8 extra steps), so that the event falls outside the timed region.
+    extra, prev = 0, None
+    while extra < 8:
+        t0 = time.perf_counter()
+        device_step(extra)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        extra += 1
+        if prev is not None and abs(dt - prev) <= 0.05 * prev:
+            break
+        prev = dt
+    barrier()
     def timed_region():
         """Exactly args.steps steps between two barriers, one CUDA-event bracket; per-step events only to spot a hiccup."""
         launches0 = _lib.launch_count()
@@ -199,7 +213,7 @@ def main():
 
     ms, per_step, fact, clocks, launches = timed_region()
     hiccup = None
-    redo = args.steps >= 2 and ms > 1.25 * args.steps * statistics.median(per_step)
+    redo = args.steps >= 3 and max(per_step) > 1.2 * statistics.median(per_step)
     if dist is not None:                                   # every rank repeats or none does
         t = torch.tensor([1.0 if redo else 0.0], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -318,7 +332,8 @@ def main():
             "config": {"workload": WORKLOAD, "batch_per_step_per_gpu": B, "rank": r, "sweeps": sweeps,
                        "l2": "inputs larger than L2: 4 x 128 MB fp32 working set per step vs 126 MB L2; two input sets alternate",
                        "parallelism": f"{world} independent ranks, disjoint weights, no data-path collective",
-                       "step_ms": [round(t, 1) for t in per_step], "remeasured_after_hiccup": hiccup},
+                       "step_ms": [round(t, 1) for t in per_step], "extra_untimed_warmup_steps": extra,
+                       "remeasured_after_hiccup": hiccup},
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
