@@ -67,9 +67,16 @@ int asvd_scaling_vector(const void* sdm, const void* fisher, int stat_dtype, int
  *   workspace          asvd_svd_workspace_bytes(m, n, batch) bytes, 256-byte aligned.  After the call it
  *                      holds the full factorisation of every weight (all min(m,n) triplets) and is the
  *                      handle asvd_svd_extract / asvd_svd_sigma read from.
- *   tol                convergence threshold on max |<x_p,x_q>| / (|x_p||x_q|); <=0 selects the default
- *   max_sweeps         <=0 selects the default
- *   sweeps_out_host    optional host int[batch]: sweeps used
+ *   tol                rotation threshold on max |<x_p,x_q>| / (|x_p||x_q|) of a block pair (pairs below it are left
+ *                      alone); a weight is finished after a sweep whose largest such cosine, measured before the
+ *                      sweep's own rotations, was below 5 tol.  <=0 selects the default (4e-6)
+ *   max_sweeps         <=0 selects the default (30)
+ *   sweeps_out_host    optional host int[batch]: sweeps used (for the 2:1 and flatter-than-that rectangles that go
+ *                      through the Gram pre-conditioner: sweeps of the square stage + sweeps of the main stage)
+ * sigma and the second factor are recovered from the ORIGINAL weight after convergence (exact bf16-plane GEMM on the
+ * tensor cores for 16-bit weights, fp32 SIMT GEMM otherwise), so they carry no accumulated rotation error.
+ * Environment switches for A/B runs (read at every call): ASVD_B200_SOLVE=quad|oddeven, ASVD_B200_POLISH=NS,
+ * ASVD_B200_GRAMPRE=0, ASVD_B200_RECOVER=simt, ASVD_B200_PRESORT=0, ASVD_B200_SIMT=1, ASVD_B200_TRACE=1.
  * Blocks the calling thread until the factorisation is complete on `stream` (it polls a convergence flag
  * once per sweep). */
 size_t asvd_svd_workspace_bytes(int m, int n, int batch);
