@@ -1222,13 +1222,60 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
   const bool solve_quad = !dbg_env && (solve_env ? solve_env[0] == 'q' : quad_pays);
   const char* simt_env = getenv("ASVD_B200_SIMT");
   const bool use_tc = !(simt_env && simt_env[0] == '1');
-  CUtensorMap tmK, tmMN;
-  if (use_tc) {
-    if (!tc::make_x_tmap(&tmK, X, p.batch, p.nv_pad, p.len_pad) || !tc::make_x_tmap_mn(&tmMN, X, p.batch, p.nv_pad, p.len_pad)) {
-      set_error("cuTensorMapEncodeTiled failed");
-      return ASVD_ERR_CUDA;
+  // Overlapped half-batches (ASVD_B200_OVERLAP=1).  The solve is a chain of 127 dependent rotation steps on one CTA per
+  // block pair: 120 us per launch whatever the batch, and its 512 threads x 128 registers fill an SM, so nothing can
+  // share that SM.  A batch of 4 x 4096^2 occupies 128 SMs with it while HBM idles; the streaming passes then want
+  // every SM.  Split in two halves on two streams, the solve of one half (64 SMs) runs beside the update + Gram
+  // passes of the other (the remaining SMs); the solves hand a token back and forth so that the two halves stay in
+  // anti-phase instead of drifting into lock-step.  Every buffer is [batch]-major, so a half is the same kernels on
+  // offset pointers (and its own tensor maps); the results are bitwise those of the single-stream schedule.
+  struct Part { int b0, nb; cudaStream_t s; CUtensorMap tmK, tmMN; };
+  Part parts[2];
+  int n_parts = 1;
+  static int sms_total = 0;
+  if (!sms_total) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms_total, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms_total <= 0)
+      sms_total = 148;
+  }
+  static cudaStream_t side[2] = {nullptr, nullptr};
+  static cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev_solve[2] = {nullptr, nullptr};
+  {
+    const char* ov_env = getenv("ASVD_B200_OVERLAP");
+    const bool want = ov_env && ov_env[0] == '1';
+    const int hb = (p.batch + 1) / 2;
+    if (want && use_tc && !g_prof_on && p.batch >= 2 && 2 * hb * p.pairs <= sms_total) {
+      if (!side[0]) {
+        for (int i = 0; i < 2; ++i) {
+          ASVD_CUDA_CHECK(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
+          ASVD_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
+          ASVD_CUDA_CHECK(cudaEventCreateWithFlags(&ev_solve[i], cudaEventDisableTiming));
+        }
+        ASVD_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+      }
+      n_parts = 2;
+      parts[0].b0 = 0; parts[0].nb = hb; parts[0].s = side[0];
+      parts[1].b0 = hb; parts[1].nb = p.batch - hb; parts[1].s = side[1];
+    } else {
+      parts[0].b0 = 0; parts[0].nb = p.batch; parts[0].s = st;
     }
   }
+  if (use_tc) {
+    for (int h = 0; h < n_parts; ++h)
+      if (!tc::make_x_tmap(&parts[h].tmK, X + parts[h].b0 * xs, parts[h].nb, p.nv_pad, p.len_pad) ||
+          !tc::make_x_tmap_mn(&parts[h].tmMN, X + parts[h].b0 * xs, parts[h].nb, p.nv_pad, p.len_pad)) {
+        set_error("cuTensorMapEncodeTiled failed");
+        return ASVD_ERR_CUDA;
+      }
+  }
+  // streaming passes of a half count on the SMs the other half's solve leaves free
+  struct BudgetGuard { ~BudgetGuard() { tc::set_sm_budget(0); } } budget_guard;
+  if (n_parts == 2) tc::set_sm_budget(sms_total - parts[0].nb * p.pairs);
+  // maxoff: per part [nb] largest cosine bits, then [nb] near-converged pair counts (the solve kernel indexes by its
+  // own gridDim.y); one part = the layout [batch][batch]
+  auto cos_idx = [&](int b) { const Part& q = parts[(n_parts == 2 && b >= parts[1].b0) ? 1 : 0]; return 2 * q.b0 + (b - q.b0); };
+  auto near_idx = [&](int b) { const Part& q = parts[(n_parts == 2 && b >= parts[1].b0) ? 1 : 0]; return 2 * q.b0 + q.nb + (b - q.b0); };
+  const int64_t track_stride = p.nb + (int64_t)p.nb * p.nb;
   const char* pre_env = getenv("ASVD_B200_TOL_PRE");   // default 5 tol = 2e-5: `tol` itself sits on the fp32 plateau, where passing is a coin flip
   float tol_pre = pre_env ? (float)atof(pre_env) : 5.f * tol;
   if (conv_tol > 0.f) tol_pre = conv_tol;          // experiments (ASVD_B200_INNER_TOL): looser tolerance for the square stage
@@ -1246,24 +1293,49 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
     // without which the threshold test could not skip converged pairs nor certify convergence
     const int gram_precise = (!use_tc || near_seen) ? 1 : 0;
     ASVD_CUDA_CHECK(cudaMemsetAsync(maxoff, 0, sizeof(unsigned) * 2 * p.batch, st));
+    if (n_parts == 2) {
+      ASVD_CUDA_CHECK(cudaEventRecord(ev_fork, st));
+      for (int h = 0; h < 2; ++h) ASVD_CUDA_CHECK(cudaStreamWaitEvent(parts[h].s, ev_fork, 0));
+    }
     for (int r = 0; r < p.rounds; ++r) {
       const int2* pr = d_pairs + (size_t)r * p.pairs;
       const int round_stamp = 2 + sweep * p.rounds + r;
       const int half_gram = (use_tc && gram_precise) ? 1 : 0;   // gram_tc_kernel's precise mode stores T, G = T + T^T
-      if (use_tc) {
-        ASVD_LAUNCH(K_GRAM, st, ASVD_CUDA_CHECK(tc::launch_gram_tc(tmK, pr, p.pairs, p.chunks, p.chunk_cols, p.len_pad, p.nv_pad, p.batch, G, done, gram_precise, track, st)));
-      } else {
-        ASVD_LAUNCH(K_GRAM, st, (gram_kernel<<<dim3(p.chunks, p.pairs, p.batch), 256, 0, st>>>(X, xs, p.len_pad, pr, p.len_pad, p.chunks, p.pairs, G, done, track, p.nb, p.chunk_cols)));
+      for (int h = 0; h < n_parts; ++h) {
+        const Part& q = parts[h];
+        cudaStream_t s = q.s;
+        float* Gq = G + (size_t)q.b0 * p.pairs * p.chunks * JK * JK;
+        float* Rq = R + (size_t)q.b0 * p.pairs * JK * JK;
+        int* flagq = flag + (size_t)q.b0 * p.pairs;
+        int* doneq = done + q.b0;
+        int* statusq = status + q.b0;
+        int* trackq = track + q.b0 * track_stride;
+        unsigned* maxoffq = maxoff + 2 * q.b0;
+        float* Xq = X + q.b0 * xs;
+        if (use_tc) {
+          ASVD_LAUNCH(K_GRAM, s, ASVD_CUDA_CHECK(tc::launch_gram_tc(q.tmK, pr, p.pairs, p.chunks, p.chunk_cols, p.len_pad, p.nv_pad, q.nb, Gq, doneq, gram_precise, trackq, s)));
+        } else {
+          ASVD_LAUNCH(K_GRAM, s, (gram_kernel<<<dim3(p.chunks, p.pairs, q.nb), 256, 0, s>>>(Xq, xs, p.len_pad, pr, p.len_pad, p.chunks, p.pairs, Gq, doneq, trackq, p.nb, p.chunk_cols)));
+        }
+        // the token: this half's solve starts when the other half's latest solve has finished
+        if (n_parts == 2 && !(r == 0 && h == 0)) ASVD_CUDA_CHECK(cudaStreamWaitEvent(s, ev_solve[h ^ 1], 0));
+        if (solve_quad)
+          ASVD_LAUNCH(K_SOLVE, s, (solve_quad_kernel<<<dim3(p.pairs, q.nb), SOLVE_THREADS, SOLVEQ_SMEM, s>>>(Gq, p.chunks, p.pairs, Rq, flagq, maxoffq, statusq, doneq, tol, polish_flag, pr, trackq, p.nb, round_stamp, gram_precise, half_gram)));
+        else
+          ASVD_LAUNCH(K_SOLVE, s, (solve_kernel<<<dim3(p.pairs, q.nb), SOLVE_THREADS, SOLVE_SMEM, s>>>(Gq, p.chunks, p.pairs, Rq, flagq, maxoffq, statusq, doneq, tol, polish_flag, dbg_steps, pr, trackq, p.nb, round_stamp, gram_precise, half_gram)));
+        if (n_parts == 2) ASVD_CUDA_CHECK(cudaEventRecord(ev_solve[h], s));
+        if (use_tc) {
+          ASVD_LAUNCH(K_UPDATE, s, ASVD_CUDA_CHECK(tc::launch_update_tc(q.tmMN, Xq, xs, p.len_pad, pr, p.pairs, p.nv_pad, p.len_pad, q.nb, Rq, flagq, doneq, s)));
+        } else {
+          const int ctas_x = (p.len_pad / 128 + UPD_TILES - 1) / UPD_TILES;
+          ASVD_LAUNCH(K_UPDATE, s, (update_kernel<<<dim3(ctas_x, p.pairs, q.nb), 256, UPDATE_SMEM, s>>>(Xq, xs, p.len_pad, pr, p.len_pad, p.pairs, Rq, flagq, doneq)));
+        }
       }
-      if (solve_quad)
-        ASVD_LAUNCH(K_SOLVE, st, (solve_quad_kernel<<<dim3(p.pairs, p.batch), SOLVE_THREADS, SOLVEQ_SMEM, st>>>(G, p.chunks, p.pairs, R, flag, maxoff, status, done, tol, polish_flag, pr, track, p.nb, round_stamp, gram_precise, half_gram)));
-      else
-        ASVD_LAUNCH(K_SOLVE, st, (solve_kernel<<<dim3(p.pairs, p.batch), SOLVE_THREADS, SOLVE_SMEM, st>>>(G, p.chunks, p.pairs, R, flag, maxoff, status, done, tol, polish_flag, dbg_steps, pr, track, p.nb, round_stamp, gram_precise, half_gram)));
-      if (use_tc) {
-        ASVD_LAUNCH(K_UPDATE, st, ASVD_CUDA_CHECK(tc::launch_update_tc(tmMN, X, xs, p.len_pad, pr, p.pairs, p.nv_pad, p.len_pad, p.batch, R, flag, done, st)));
-      } else {
-        const int ctas_x = (p.len_pad / 128 + UPD_TILES - 1) / UPD_TILES;
-        ASVD_LAUNCH(K_UPDATE, st, (update_kernel<<<dim3(ctas_x, p.pairs, p.batch), 256, UPDATE_SMEM, st>>>(X, xs, p.len_pad, pr, p.len_pad, p.pairs, R, flag, done)));
+    }
+    if (n_parts == 2) {
+      for (int h = 0; h < 2; ++h) {
+        ASVD_CUDA_CHECK(cudaEventRecord(ev_join[h], parts[h].s));
+        ASVD_CUDA_CHECK(cudaStreamWaitEvent(st, ev_join[h], 0));
       }
     }
     ASVD_CUDA_CHECK(cudaGetLastError());
@@ -1275,7 +1347,7 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
     for (int b = 0; b < p.batch; ++b) {
       if (h_done[b]) continue;
       float mo;
-      memcpy(&mo, &h_maxoff[b], 4);
+      memcpy(&mo, &h_maxoff[cos_idx(b)], 4);
       h_sweeps[b] = sweep + 1;
       // a sweep measured with the single-pass Gram cannot certify convergence
       // mo is the largest cosine met at VISIT time, i.e. before this sweep's own rotations (every pair at or above
@@ -1292,7 +1364,7 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
         // 1329 of 2016), power-law spectra with kappa >= 5e3 have 2-4 of 2016; the bar is 5 %.  The stage's unit vectors are an
         // orthogonal transform only once it HAS converged, so there is no partial credit: give up early and let the
         // caller take the direct path.
-        const unsigned near_pairs = h_maxoff[p.batch + b];
+        const unsigned near_pairs = h_maxoff[near_idx(b)];
         static const char* gu_env = getenv("ASVD_B200_INNER_GIVEUP");          // 0: never give up (diagnostics)
         if (!(gu_env && gu_env[0] == '0') &&
             ((sweep == 3 && mo > 0.25f) ||          // healthy: <= 0.09 after four sweeps; stalled: 0.45-0.9
@@ -1301,14 +1373,14 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
       }
       if (finished) { h_done[b] = 1; changed = true; }
       else { all_done = false; worst = fmaxf(worst, mo); best = fminf(best, mo); }
-      if (h_maxoff[p.batch + b] > 0) near_seen = true;
+      if (h_maxoff[near_idx(b)] > 0) near_seen = true;
     }
     (void)worst; (void)best;
     if (getenv("ASVD_B200_TRACE")) {                 // diagnostic: convergence trace, one line per sweep
       fprintf(stderr, "sweep %2d precise %d  max|cos|:", sweep + 1, gram_precise);
-      for (int b = 0; b < p.batch; ++b) { float mo; memcpy(&mo, &h_maxoff[b], 4); fprintf(stderr, " %.3e", mo); }
+      for (int b = 0; b < p.batch; ++b) { float mo; memcpy(&mo, &h_maxoff[cos_idx(b)], 4); fprintf(stderr, " %.3e", mo); }
       fprintf(stderr, "  near-orthogonal pairs:");
-      for (int b = 0; b < p.batch; ++b) fprintf(stderr, " %u", h_maxoff[p.batch + b]);
+      for (int b = 0; b < p.batch; ++b) fprintf(stderr, " %u", h_maxoff[near_idx(b)]);
       fprintf(stderr, "\n");
     }
     if (gave_up) break;

@@ -456,13 +456,15 @@ update_tc_kernel(const __grid_constant__ CUtensorMap tmX, float* __restrict__ X,
 
 // ------------------------------------------------------------------------------------------------ host
 static int g_sms = 0;
+static thread_local int g_sm_budget = 0;   // > 0: SMs the streaming passes may count on (the rest run another half's solve)
+void set_sm_budget(int sms) { g_sm_budget = sms; }
 static int sm_count() {
   if (!g_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  return g_sms;
+  return (g_sm_budget > 0 && g_sm_budget < g_sms) ? g_sm_budget : g_sms;
 }
 
 // tensor map over the block-tiled X of the whole batch, viewed as [batch * nv_pad * len_pad / 32 rows, 32 cols] fp32:

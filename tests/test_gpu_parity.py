@@ -407,3 +407,27 @@ def test_recovery_tensor_core_matches_simt(monkeypatch):
     A1, B1 = a.extract(460, "UV", torch.float32)
     A2, B2 = b.extract(460, "UV", torch.float32)
     assert ((A1 @ B1 - A2 @ B2) * scale).norm().item() / ((A2 @ B2) * scale).norm().item() < 1e-4
+
+
+@pytest.mark.parametrize("m,n,batch", [(1024, 1024, 4), (768, 1280, 3), (2560, 1024, 2)])
+def test_overlapped_half_batches_bitwise(m, n, batch, monkeypatch):
+    """ASVD_B200_OVERLAP=1 runs the two halves of a batch on two streams (the solve of one half beside the streaming
+    passes of the other).  Same kernels on offset pointers: the factors must be bitwise those of the one-stream
+    schedule, for even and odd batches, square, wide and Gram-pre-conditioned tall shapes."""
+    L = _lib()
+    Ws, Ss = [], []
+    for b in range(batch):
+        W, s = O.synthetic_weight(m, n, seed=40 + b)
+        Ws.append(W.cuda()); Ss.append((s ** 0.5 + 1e-6).float().cuda())
+    monkeypatch.setenv("ASVD_B200_OVERLAP", "0")
+    ref = L.scaled_svd(Ws, Ss)
+    monkeypatch.setenv("ASVD_B200_OVERLAP", "1")
+    for _ in range(2):                      # twice: the second run reuses the side streams and events
+        got = L.scaled_svd(Ws, Ss)
+        r = min(m, n) // 2
+        for b in range(batch):
+            assert torch.equal(ref.sigma(b), got.sigma(b))
+            A1, B1 = ref.extract(r, "UV", torch.float16, b)
+            A2, B2 = got.extract(r, "UV", torch.float16, b)
+            assert torch.equal(A1, A2) and torch.equal(B1, B2)
+    assert ref.sweeps == got.sweeps
