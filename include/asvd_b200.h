@@ -76,7 +76,8 @@ int asvd_scaling_vector(const void* sdm, const void* fisher, int stat_dtype, int
  * sigma and the second factor are recovered from the ORIGINAL weight after convergence (exact bf16-plane GEMM on the
  * tensor cores for 16-bit weights, fp32 SIMT GEMM otherwise), so they carry no accumulated rotation error.
  * Environment switches for A/B runs (read at every call): ASVD_B200_SOLVE=quad|oddeven, ASVD_B200_POLISH=NS,
- * ASVD_B200_GRAMPRE=0, ASVD_B200_RECOVER=simt, ASVD_B200_PRESORT=0, ASVD_B200_SIMT=1, ASVD_B200_TRACE=1.
+ * ASVD_B200_GRAMPRE=0, ASVD_B200_RECOVER=simt, ASVD_B200_PRESORT=0, ASVD_B200_SIMT=1, ASVD_B200_TRACE=1,
+ * ASVD_B200_OVERLAP=1 (two half-batches on two internal streams; same results bitwise, measured not faster).
  * Blocks the calling thread until the factorisation is complete on `stream` (it polls a convergence flag
  * once per sweep). */
 size_t asvd_svd_workspace_bytes(int m, int n, int batch);
