@@ -4,7 +4,7 @@
 Additions are namespaced and optional: `--calib_dataset synthetic` (random token ids; the box has no datasets),
 `--synthetic_model {opt-125m,llama-2-7b,llama-2-13b}` (random-init architecture instead of a checkpoint) and
 multi-GPU through torchrun (layers sharded per asvd4llm_b200.sharding).  Out of scope here, as in SURVEY.md §2:
-fisher calibration, quantization, the lm-eval harness (`--eval_*` are accepted and reported as skipped).
+quantization and the lm-eval harness (`--eval_*` are accepted and reported as skipped).
 """
 import argparse
 import os
@@ -12,10 +12,10 @@ import os
 import numpy as np
 import torch
 
-from asvd4llm_b200.act_aware_utils import calib_input_distribution
+from asvd4llm_b200.act_aware_utils import calib_fisher_info, calib_input_distribution
 from asvd4llm_b200.binary_search import binary_search_truncation_rank, search_allocation
 from asvd4llm_b200.evaluate_utils import evaluate_perplexity
-from asvd4llm_b200.sensitivity import calib_sensitivity_ppl
+from asvd4llm_b200.sensitivity import calib_sensitivity_ppl, calib_sensitivity_stable_rank
 from asvd4llm_b200 import sharding
 
 SYNTHETIC = {
@@ -74,13 +74,18 @@ def main(args):
     if not args.raw_model:
         calib_loader = get_calib_data(args, tokenizer, model.config.vocab_size)
         if "fisher" in args.scaling_method:
-            raise SystemExit("fisher calibration is out of scope of the B200 path (SURVEY.md §2); fisher_info attributes "
-                             "set by upstream's calib_fisher_info are honoured by SVDLinear.from_linear")
+            calib_fisher_info(model, calib_loader, args.use_cache)
         if "abs" in args.scaling_method:
             calib_input_distribution(model, calib_loader, args.scaling_method, args.use_cache)
-        if args.sensitivity_metric != "ppl":
-            raise SystemExit("stable_rank sensitivity is out of scope (SURVEY.md §2)")
-        if world == 1:
+        if args.sensitivity_metric == "stable_rank":
+            # one sigma-only factorisation per linear (no model forwards): every rank computes the whole table
+            sensitivity = calib_sensitivity_stable_rank(model, calib_loader, args, args.use_cache)
+            if world == 1:
+                binary_search_truncation_rank(model, sensitivity, calib_loader, args)
+            else:
+                chosen, default = search_allocation(model, sensitivity, calib_loader, args)
+                sharding.decompose_sharded(model, chosen, default, args)
+        elif world == 1:
             sensitivity = calib_sensitivity_ppl(model, calib_loader, args, args.use_cache)
             binary_search_truncation_rank(model, sensitivity, calib_loader, args)
         else:

@@ -15,7 +15,7 @@ from . import build as _build
 
 F32, F16, BF16 = 0, 1, 2
 FUSE = {"UV": 0, "U": 1, "V": 2}
-STAT_ABS_MEAN, STAT_ABS_MAX = 0, 1
+STAT_ABS_MEAN, STAT_ABS_MAX, STAT_SQ_MEAN = 0, 1, 2
 OK, ERR_INVALID, ERR_WORKSPACE, ERR_CUDA, ERR_NONFINITE, ERR_NOT_CONVERGED = 0, 1, 2, 3, 4, 5
 
 _DTYPES = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
@@ -221,7 +221,8 @@ def lowrank_forward(x: torch.Tensor, A: torch.Tensor, B: torch.Tensor, bias: Opt
 
 
 def absstat_accum(x: torch.Tensor, acc: torch.Tensor, method: str) -> None:
-    """One hook call of act_aware_utils.py:64-74: acc [n] (same dtype as x) updated in place from x [.., L, n]."""
+    """One hook call of act_aware_utils.py:64-74: acc [n] (same dtype as x) updated in place from x [.., L, n].
+    method "sq_mean" is the Fisher statistic of act_aware_utils.py:31 (x = a weight gradient [m, n])."""
     _require_cuda(x, acc)
     lib = load()
     n = x.shape[-1]
@@ -230,7 +231,14 @@ def absstat_accum(x: torch.Tensor, acc: torch.Tensor, method: str) -> None:
         x2 = x2.contiguous()
     if acc.dtype != x.dtype or acc.numel() != n or not acc.is_contiguous():
         raise ValueError("acc must be a contiguous [n] tensor of the activation dtype")
-    mode = STAT_ABS_MEAN if "abs_mean" in method else STAT_ABS_MAX
+    if method == "sq_mean":
+        mode = STAT_SQ_MEAN
+    elif "abs_mean" in method:
+        mode = STAT_ABS_MEAN
+    elif "abs_max" in method:
+        mode = STAT_ABS_MAX
+    else:
+        raise ValueError(f"unknown statistic {method!r}")
     nbytes = lib.asvd_absstat_scratch_bytes(n)
     scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device):

@@ -1,6 +1,8 @@
 """calib_input_distribution — upstream act_aware_utils.py:47-95 with the hook arithmetic (:64-74) in the
-asvd_absstat_accum kernel.  Cache file name and format are upstream's:
-cache/{model_id with / -> _}_calib_input_distribution_{method}.pt = {module name: Tensor[in_features]}."""
+asvd_absstat_accum kernel — and calib_fisher_info — act_aware_utils.py:8-44 with the per-sample reduction of
+the weight gradient (:31) in the same kernel.  Cache file names and formats are upstream's:
+cache/{model_id with / -> _}_calib_input_distribution_{method}.pt and ..._calib_fisher_info.pt, each
+{module name: Tensor[in_features]}."""
 import os
 
 import torch
@@ -51,4 +53,48 @@ def calib_input_distribution(model, calib_loader, method, use_cache=True):
         if isinstance(module, nn.Linear):
             module._forward_hooks.clear()                      # upstream clears every hook (:93)
             table[name] = module.scaling_diag_matrix
+    torch.save(table, cache_file)
+
+
+def calib_fisher_info(model, calib_loader, use_cache=True):
+    """Upstream act_aware_utils.py:8-44: fisher_info[j] = sqrt(mean over samples of mean_i (dL/dW[i, j])^2).
+    The backward pass is the model's own (autograd, as upstream); the [m, n] -> [n] reduction of every weight
+    gradient runs in asvd_absstat_accum (SQ_MEAN) instead of `grad.pow(2).mean(0)`, which materialises an
+    [m, n] temporary per linear and sample."""
+    model_id = model.config._name_or_path
+    cache_file = f"cache/{model_id.replace('/', '_')}_calib_fisher_info.pt"
+    if os.path.exists(cache_file) and use_cache:
+        table = torch.load(cache_file, map_location="cpu")
+        for name, module in model.named_modules():
+            if isinstance(module, nn.Linear):
+                module.fisher_info = table[name].to(module.weight.device)
+        return
+    model.eval()
+    linears = [(name, module) for name, module in model.named_modules() if isinstance(module, nn.Linear)]
+    for _, module in linears:
+        module.fisher_info = 0
+    device = getattr(model, "device", None) or next(model.parameters()).device
+    for batch in calib_loader:
+        input_ids = batch["input_ids"][:, :-1].to(device)
+        labels = batch["input_ids"][:, 1:].to(device)
+        with torch.enable_grad():
+            out = model(input_ids=input_ids, labels=labels)
+            out[0].backward()
+        with torch.no_grad():
+            for _, module in linears:
+                g = module.weight.grad
+                if g is None:                                   # upstream would raise AttributeError here (:31)
+                    raise AttributeError("'NoneType' object has no attribute 'detach'")
+                acc = module.fisher_info
+                if not torch.is_tensor(acc):                    # python int 0 until the first sample (:21)
+                    acc = torch.zeros(g.shape[1], dtype=g.dtype, device=g.device)
+                    module.fisher_info = acc
+                _lib.absstat_accum(g.detach(), acc, "sq_mean")
+        model.zero_grad()
+    table = {}
+    with torch.no_grad():
+        for name, module in linears:
+            module.fisher_info = module.fisher_info.div(len(calib_loader)).sqrt()     # :36
+            module._forward_hooks.clear()                                             # :42
+            table[name] = module.fisher_info
     torch.save(table, cache_file)

@@ -35,7 +35,8 @@ __global__ void scaling_vector_kernel(const T* __restrict__ sdm, const T* __rest
 }
 
 // ------------------------------------------------------------------------------------------------ a1
-// act_aware_utils.py:64-74.  Stage 1: per-column partial sum / max of |x| over a slab of rows.
+// act_aware_utils.py:64-74 (abs_mean / abs_max of an activation) and :31 (mean of squares of a weight gradient, the
+// Fisher statistic).  Stage 1: per-column partial sum / max of |x| (or sum of x^2) over a slab of rows.
 constexpr int STAT_SPLITS = 32;
 
 template <typename T>
@@ -66,7 +67,12 @@ __global__ void __launch_bounds__(256) absstat_partial_kernel(const T* __restric
       if (ok0) v0 = fabsf(to_f32<T>(p[0]));
       if (ok1) v1 = fabsf(to_f32<T>(p[1]));
     }
-    if (mode == ASVD_STAT_ABS_MEAN) { a0 += v0; a1 += v1; }
+    if (mode == ASVD_STAT_SQ_MEAN) {
+      // act_aware_utils.py:31 `grad.pow(2)` is a tensor of the gradient's dtype: each square is rounded to T
+      // (fp16 squares below 6e-8 flush, as they do upstream) before the fp32 sum of `.mean(0)`
+      v0 = to_f32<T>(from_f32<T>(v0 * v0)); v1 = to_f32<T>(from_f32<T>(v1 * v1));
+    }
+    if (mode != ASVD_STAT_ABS_MAX) { a0 += v0; a1 += v1; }
     else {
       // NaN-propagating max, like torch.amax
       a0 = (v0 != v0 || a0 != a0) ? NAN : fmaxf(a0, v0);
@@ -80,7 +86,7 @@ __global__ void __launch_bounds__(256) absstat_partial_kernel(const T* __restric
     float v = red[0][c];
     for (int r = 1; r < 4; ++r) {
       float w = red[r][c];
-      if (mode == ASVD_STAT_ABS_MEAN) v += w;
+      if (mode != ASVD_STAT_ABS_MAX) v += w;
       else v = (v != v || w != w) ? NAN : fmaxf(v, w);
     }
     const int col = blockIdx.x * 128 + c;
@@ -95,13 +101,13 @@ __global__ void absstat_combine_kernel(const float* __restrict__ partial, int n,
   float v = partial[j];
   for (int s = 1; s < STAT_SPLITS; ++s) {
     float w = partial[(int64_t)s * n + j];
-    if (mode == ASVD_STAT_ABS_MEAN) v += w;
+    if (mode != ASVD_STAT_ABS_MAX) v += w;
     else v = (v != v || w != w) ? NAN : fmaxf(v, w);
   }
   float old = to_f32<T>(acc[j]);
-  if (mode == ASVD_STAT_ABS_MEAN) {
-    float mean = to_f32<T>(from_f32<T>(v / (float)L));     // abs().mean(dim=-2) in the activation dtype
-    acc[j] = from_f32<T>(old + mean);                      // scaling_diag_matrix += abs_mean
+  if (mode != ASVD_STAT_ABS_MAX) {
+    float mean = to_f32<T>(from_f32<T>(v / (float)L));     // abs().mean(dim=-2) / pow(2).mean(0) in the tensor's dtype
+    acc[j] = from_f32<T>(old + mean);                      // scaling_diag_matrix += abs_mean / fisher_info += ...
   } else {
     float cur = to_f32<T>(from_f32<T>(v));
     acc[j] = from_f32<T>(cur > old ? cur : old);           // torch.where(abs_max > acc, abs_max, acc)
@@ -172,7 +178,7 @@ size_t asvd_absstat_scratch_bytes(int n) { return n > 0 ? sizeof(float) * (size_
 int asvd_absstat_accum(const void* x, int64_t ldx, int64_t L, int n, int dtype, int mode, void* acc, void* scratch,
                        size_t scratch_bytes, void* stream) {
   ASVD_REQUIRE(x && acc && scratch && L > 0 && n > 0 && ldx >= n, "bad argument");
-  ASVD_REQUIRE(mode == ASVD_STAT_ABS_MEAN || mode == ASVD_STAT_ABS_MAX, "bad mode %d", mode);
+  ASVD_REQUIRE(mode == ASVD_STAT_ABS_MEAN || mode == ASVD_STAT_ABS_MAX || mode == ASVD_STAT_SQ_MEAN, "bad mode %d", mode);
   if (scratch_bytes < asvd_absstat_scratch_bytes(n)) { set_error("scratch too small"); return ASVD_ERR_WORKSPACE; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float* partial = reinterpret_cast<float*>(scratch);

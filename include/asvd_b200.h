@@ -25,7 +25,7 @@ enum { ASVD_F32 = 0, ASVD_F16 = 1, ASVD_BF16 = 2 };
 /* sigma_fuse modes — modules/svd_linear.py:16-24 */
 enum { ASVD_FUSE_UV = 0, ASVD_FUSE_U = 1, ASVD_FUSE_V = 2 };
 /* calibration statistic — act_aware_utils.py:64-74 */
-enum { ASVD_STAT_ABS_MEAN = 0, ASVD_STAT_ABS_MAX = 1 };
+enum { ASVD_STAT_ABS_MEAN = 0, ASVD_STAT_ABS_MAX = 1, ASVD_STAT_SQ_MEAN = 2 };
 /* status codes */
 enum {
   ASVD_OK = 0,
@@ -110,6 +110,8 @@ int asvd_lowrank_forward(const void* x, int64_t ldx, int64_t M, int n, const voi
 /* ---- a1: calibration statistic of one hook call — act_aware_utils.py:64-74.
  * x [L, n] ldx in `dtype`; acc [n] in the same dtype (upstream accumulates in the activation dtype).
  *   ABS_MEAN: acc[j] = rnd(acc[j] + rnd(mean_i |x[i,j]|));  ABS_MAX: acc[j] = max(acc[j], max_i |x[i,j]|)
+ *   SQ_MEAN:  acc[j] = rnd(acc[j] + rnd(mean_i rnd(x[i,j]^2))) — the Fisher statistic of calib_fisher_info,
+ *             act_aware_utils.py:31 (`fisher_info += weight.grad.pow(2).mean(0)`), x = the [m, n] weight gradient
  * scratch: asvd_absstat_scratch_bytes(n) bytes. */
 size_t asvd_absstat_scratch_bytes(int n);
 int asvd_absstat_accum(const void* x, int64_t ldx, int64_t L, int n, int dtype, int mode, void* acc,

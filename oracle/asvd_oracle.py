@@ -177,6 +177,32 @@ def calib_input_distribution(model: nn.Module, calib_loader, method: str) -> Dic
     return {name: mod.scaling_diag_matrix for name, mod in model.named_modules() if isinstance(mod, nn.Linear)}
 
 
+def fisher_stat_update(acc, grad: torch.Tensor):
+    """act_aware_utils.py:31 — one sample's contribution: acc += grad.pow(2).mean(0), in the gradient's dtype."""
+    return acc + grad.detach().pow(2).mean(0)
+
+
+def calib_fisher_info(model: nn.Module, calib_loader) -> Dict[str, torch.Tensor]:
+    """act_aware_utils.py:8-44 without the cache file: fisher_info = sqrt(sum_samples mean_i grad[i, :]^2 / N).
+    Returns {module name: Tensor[n]} and sets module.fisher_info."""
+    model.eval()
+    linears = [(n, m) for n, m in model.named_modules() if isinstance(m, nn.Linear)]
+    for _, mod in linears:
+        mod.fisher_info = 0
+    dev = next(model.parameters()).device
+    for batch in calib_loader:
+        input_ids = batch["input_ids"][:, :-1].to(dev)
+        labels = batch["input_ids"][:, 1:].to(dev)
+        out = model(input_ids=input_ids, labels=labels)
+        out[0].backward()
+        for _, mod in linears:
+            mod.fisher_info = fisher_stat_update(mod.fisher_info, mod.weight.grad)
+        model.zero_grad()
+    for _, mod in linears:
+        mod.fisher_info = mod.fisher_info.div(len(calib_loader)).sqrt()
+    return {n: m.fisher_info for n, m in linears}
+
+
 # ----------------------------------------------------------------------------- a10: perplexity
 @torch.no_grad()
 def evaluate_perplexity(model, dataset: torch.Tensor, limit: int) -> float:

@@ -431,3 +431,56 @@ def test_overlapped_half_batches_bitwise(m, n, batch, monkeypatch):
             A2, B2 = got.extract(r, "UV", torch.float16, b)
             assert torch.equal(A1, A2) and torch.equal(B1, B2)
     assert ref.sweeps == got.sweeps
+
+
+def test_fisher_info_against_upstream_golden(golden_pipeline, tmp_path, monkeypatch):
+    """calib_fisher_info (upstream act_aware_utils.py:8-44): the weight-gradient reduction runs in
+    asvd_absstat_accum(SQ_MEAN); values, cache file name and keys are upstream's; a second call reads the cache."""
+    import os
+    from conftest import GOLDEN
+    from asvd4llm_b200.act_aware_utils import calib_fisher_info
+    gold = torch.load(os.path.join(GOLDEN, "tiny_opt_fisher.pt"), weights_only=False)
+    monkeypatch.chdir(tmp_path); os.makedirs("cache")
+    model = build_tiny_opt(golden_pipeline).cuda()
+    n0 = _lib().launch_count()
+    calib_fisher_info(model, golden_pipeline["loader"], use_cache=False)
+    assert _lib().launch_count() > n0
+    assert sorted(os.listdir("cache")) == gold["cache_files"]
+    table = torch.load(os.path.join("cache", gold["cache_files"][0]), map_location="cpu")
+    assert list(table.keys()) == gold["cache_keys"]
+    for name, mod in model.named_modules():
+        if isinstance(mod, nn.Linear):
+            want = gold["fisher_info"][name]
+            assert mod.fisher_info.dtype == want.dtype and mod.fisher_info.is_cuda
+            assert torch.allclose(mod.fisher_info.cpu(), want, rtol=2e-3, atol=1e-9), name    # GPU backward vs CPU backward
+            assert torch.equal(table[name], mod.fisher_info.cpu())
+    model2 = build_tiny_opt(golden_pipeline).cuda()
+    n1 = _lib().launch_count()
+    calib_fisher_info(model2, golden_pipeline["loader"], use_cache=True)
+    assert _lib().launch_count() == n1
+    assert torch.equal(dict(model2.named_modules())["lm_head"].fisher_info.cpu(), table["lm_head"])
+    # the factorisation honours both statistics (scaling_method fisher_abs_mean)
+    c = gold["from_linear"]
+    lin = dict(model.named_modules())[c["layer"]]
+    lin.scaling_diag_matrix = golden_pipeline["sdm_abs_mean"][c["layer"]].cuda()
+    from asvd4llm_b200 import SVDLinear
+    mod = SVDLinear.from_linear(lin, c["ratio"], act_aware=True, alpha=c["alpha"])
+    assert mod.truncation_rank == c["truncation_rank"]
+    ref = c["A"].double() @ c["B"].double()
+    got = mod.ALinear.weight.data.double().cpu() @ mod.BLinear.weight.data.double().cpu()
+    assert (got - ref).abs().max().item() < 1e-3 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.bfloat16])
+def test_sq_mean_matches_torch_expression(dtype):
+    """SQ_MEAN restates `acc += g.pow(2).mean(0)` with upstream's roundings (square in the gradient dtype, fp32 sum,
+    mean and accumulator rounded to the dtype), on a ragged shape with tiny values that flush in fp16."""
+    L = _lib()
+    g = torch.Generator().manual_seed(11)
+    G = (torch.randn(333, 1001, generator=g) * torch.logspace(-5, 0, 1001)).to(dtype)
+    acc0 = torch.rand(1001, generator=g).to(dtype) * 1e-2
+    want = O.fisher_stat_update(acc0.clone(), G)
+    acc = acc0.clone().cuda()
+    L.absstat_accum(G.cuda(), acc, "sq_mean")
+    tol = {torch.float16: 1e-3, torch.bfloat16: 8e-3, torch.float32: 2e-6}[dtype]
+    assert torch.allclose(acc.cpu().float(), want.float(), rtol=tol, atol=1e-12)

@@ -126,3 +126,33 @@ def test_allocation_matches_upstream(golden_pipeline):
     mods = dict(model.named_modules())
     got = {k: min(O.rank_for_ratio(*mods[k].weight.shape, r), min(mods[k].weight.shape)) for k, r in chosen.items() if r != 2}
     assert got == golden_pipeline["kv_truncation_ranks"]
+
+
+@pytest.fixture(scope="module")
+def golden_fisher():
+    import os
+    from conftest import GOLDEN
+    return torch.load(os.path.join(GOLDEN, "tiny_opt_fisher.pt"), weights_only=False)
+
+
+def test_fisher_info_matches_upstream(golden_pipeline, golden_fisher):
+    """act_aware_utils.py:8-44 (tests/golden/make_golden_fisher.py ran the upstream function on the same model)."""
+    model = build_tiny_opt(golden_pipeline)
+    got = O.calib_fisher_info(model, golden_pipeline["loader"])
+    want = golden_fisher["fisher_info"]
+    assert list(got.keys()) == list(want.keys()) == golden_fisher["cache_keys"]
+    for k in want:
+        assert got[k].dtype == want[k].dtype and got[k].shape == want[k].shape, k
+        assert torch.allclose(got[k], want[k], rtol=1e-4, atol=1e-9), k        # autograd + host BLAS reassociation
+
+
+def test_fisher_and_abs_mean_scaling_matches_upstream(golden_pipeline, golden_fisher):
+    """svd_linear.py:48-59 with both statistics present (scaling_method fisher_abs_mean), full rank: exact."""
+    c = golden_fisher["from_linear"]
+    model = build_tiny_opt(golden_pipeline)
+    lin = dict(model.named_modules())[c["layer"]]
+    out = O.factorise_exact(lin.weight.data, c["ratio"], sdm=golden_pipeline["sdm_abs_mean"][c["layer"]],
+                            fisher=golden_fisher["fisher_info"][c["layer"]], alpha=c["alpha"], act_aware=True)
+    assert out["rank"] == c["truncation_rank"]
+    ref = c["A"].double() @ c["B"].double()
+    assert (out["A"].double() @ out["B"].double() - ref).abs().max().item() < 1e-4 * ref.abs().max().item()
