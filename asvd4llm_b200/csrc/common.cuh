@@ -29,6 +29,16 @@ void set_error(const char* fmt, ...);
     }                                  \
   } while (0)
 
+// Function attributes, __constant__ tables, streams and events belong to a device (context): one-time set-up is
+// tracked per device, so that one process may factorise layers that live on several GPUs (upstream loads models with
+// device_map="auto").  Races between host threads are benign: the guarded calls are idempotent.
+constexpr int ASVD_MAX_DEVICES = 64;
+static inline int current_device_slot() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= ASVD_MAX_DEVICES) d = 0;
+  return d;
+}
+
 // kernel classes for launch counting / optional per-class CUDA-event timing (asvd_profile_*)
 enum Kind { K_PREP = 0, K_GRAM, K_SOLVE, K_UPDATE, K_FINAL, K_EXTRACT, K_FORWARD, K_STAT, K_COUNT };
 void prof_begin(int kind, cudaStream_t st);

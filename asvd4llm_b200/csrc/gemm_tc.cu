@@ -253,11 +253,12 @@ static cudaError_t launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, con
                              int K, int sms, cudaStream_t st, float* Cf = nullptr, int64_t ldcf = 0, const float* cscale = nullptr,
                              const KSched* sched = nullptr) {
   using S = GemmSmem<BN, NBUF>;
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[ASVD_MAX_DEVICES] = {};
+  const int dev = current_device_slot();
+  if (!attr[dev]) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<T, BN, NBUF, F32OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr[dev] = true;
   }
   const int pairs = (((M + BM - 1) / BM + 1) / 2) * ((N + BN - 1) / BN);
   const int nclusters = pairs < sms / 2 ? pairs : sms / 2;

@@ -1168,7 +1168,9 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
   int* track = reinterpret_cast<int*>(ws + p.off_track);
   const int64_t xs = (int64_t)p.nv_pad * p.len_pad;
 
-  static bool attrs_set = false;
+  static bool attrs_set_dev[ASVD_MAX_DEVICES] = {};
+  const int dev_slot = current_device_slot();
+  bool& attrs_set = attrs_set_dev[dev_slot];
   if (!attrs_set) {
     ASVD_CUDA_CHECK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
     ASVD_CUDA_CHECK(cudaFuncSetAttribute(solve_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVEQ_SMEM));
@@ -1238,8 +1240,11 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms_total, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms_total <= 0)
       sms_total = 148;
   }
-  static cudaStream_t side[2] = {nullptr, nullptr};
-  static cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev_solve[2] = {nullptr, nullptr};
+  struct SideStreams { cudaStream_t side[2]; cudaEvent_t fork, join[2], solve[2]; };
+  static SideStreams side_dev[ASVD_MAX_DEVICES] = {};
+  SideStreams& ss = side_dev[dev_slot];
+  cudaStream_t* side = ss.side;
+  cudaEvent_t &ev_fork = ss.fork, *ev_join = ss.join, *ev_solve = ss.solve;
   {
     const char* ov_env = getenv("ASVD_B200_OVERLAP");
     const bool want = ov_env && ov_env[0] == '1';

@@ -212,12 +212,13 @@ static bool build_quad_schedule(unsigned char* tab /* [(QROUNDS-1)*32] */) {
   return true;
 }
 static cudaError_t upload_quad_schedule() {
-  static bool done = false;
-  if (done) return cudaSuccess;
+  static bool done[ASVD_MAX_DEVICES] = {};
+  const int dev = current_device_slot();
+  if (done[dev]) return cudaSuccess;
   unsigned char tab[(QROUNDS - 1) * 32];
   if (!build_quad_schedule(tab)) return cudaErrorUnknown;
   cudaError_t e = cudaMemcpyToSymbol(c_quad_src, tab, sizeof(tab));
-  if (e == cudaSuccess) done = true;
+  if (e == cudaSuccess) done[dev] = true;
   return e;
 }
 

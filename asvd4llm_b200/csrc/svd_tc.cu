@@ -475,11 +475,12 @@ bool make_x_tmap(CUtensorMap* map, const float* X, int batch, int nv_pad, int le
 
 cudaError_t launch_gram_tc(const CUtensorMap& tmX, const int2* pairs, int pairs_per_mat, int chunks, int chunk_cols,
                            int len_pad, int nv_pad, int batch, float* Gpart, const int* done, int precise, const int* track, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[ASVD_MAX_DEVICES] = {};
+  const int dev = current_device_slot();
+  if (!attr[dev]) {
     cudaError_t e = cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr[dev] = true;
   }
   const int n_items = batch * pairs_per_mat * chunks;
   const int grid = n_items < sm_count() ? n_items : sm_count();
@@ -498,11 +499,12 @@ bool make_x_tmap_mn(CUtensorMap* map, const float* X, int batch, int nv_pad, int
 cudaError_t launch_update_tc(const CUtensorMap& tmX, float* X, int64_t mat_stride, int ldx, const int2* pairs,
                              int pairs_per_mat, int nv_pad, int len_pad, int batch, const float* R, const int* pairflag,
                              const int* done, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[ASVD_MAX_DEVICES] = {};
+  const int dev = current_device_slot();
+  if (!attr[dev]) {
     cudaError_t e = cudaFuncSetAttribute(update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UP_SMEM);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr[dev] = true;
   }
   const char* dbg_env = getenv("ASVD_B200_DBG_UPDATE");      // timing experiments only
   const int dbg = dbg_env ? atoi(dbg_env) : 0;

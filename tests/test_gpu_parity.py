@@ -484,3 +484,30 @@ def test_sq_mean_matches_torch_expression(dtype):
     L.absstat_accum(G.cuda(), acc, "sq_mean")
     tol = {torch.float16: 1e-3, torch.bfloat16: 8e-3, torch.float32: 2e-6}[dtype]
     assert torch.allclose(acc.cpu().float(), want.float(), rtol=tol, atol=1e-12)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_layers_on_two_devices_in_one_process():
+    """Upstream loads models with device_map="auto": one process, linears spread over several GPUs.  Function
+    attributes, the quad schedule table and the side streams are per-device state; factors and the forward must be
+    the same on every device (cuda:1 first, so that nothing was initialised by an earlier test on that device)."""
+    from asvd4llm_b200 import SVDLinear
+    outs = []
+    for dev in ("cuda:1", "cuda:0"):
+        torch.manual_seed(0)
+        W, s = O.synthetic_weight(640, 512, seed=77)
+        lin = nn.Linear(512, 640, bias=True).half()
+        lin.weight.data = W
+        lin.scaling_diag_matrix = s.half()
+        lin = lin.to(dev)
+        lin.scaling_diag_matrix = lin.scaling_diag_matrix.to(dev)
+        mod = SVDLinear.from_linear(lin, 0.8, act_aware=True, alpha=0.5)
+        assert mod.ALinear.weight.device == torch.device(dev)
+        x = (torch.randn(3, 40, 512, generator=torch.Generator().manual_seed(1)) * 0.125).half().to(dev)
+        y = mod(x)
+        acc = torch.zeros(512, dtype=torch.float16, device=dev)
+        _lib().absstat_accum(x, acc, "abs_mean")
+        torch.cuda.synchronize(dev)
+        outs.append((mod.ALinear.weight.data.cpu(), mod.BLinear.weight.data.cpu(), y.cpu(), acc.cpu()))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
