@@ -122,8 +122,9 @@ def scaling_vector(sdm: Optional[torch.Tensor], fisher: Optional[torch.Tensor], 
     fisher = None if fisher is None else fisher.to(device).contiguous()
     _require_cuda(sdm, fisher)
     out = torch.empty(n, dtype=torch.float32, device=device)
-    _check(load().asvd_scaling_vector(None if sdm is None else sdm.data_ptr(), None if fisher is None else fisher.data_ptr(),
-                                      code, n, float(alpha), out.data_ptr(), _stream()))
+    with torch.cuda.device(out.device):          # launch on the tensors' device, not the process' current one
+        _check(load().asvd_scaling_vector(None if sdm is None else sdm.data_ptr(), None if fisher is None else fisher.data_ptr(),
+                                          code, n, float(alpha), out.data_ptr(), _stream()))
     return out
 
 
@@ -136,7 +137,8 @@ class Factorisation:
 
     def sigma(self, b: int = 0) -> torch.Tensor:
         out = torch.empty(min(self.m, self.n), dtype=torch.float32, device=self.workspace.device)
-        _check(load().asvd_svd_sigma(self.workspace.data_ptr(), self.m, self.n, self.batch, b, out.data_ptr(), _stream()))
+        with torch.cuda.device(self.workspace.device):
+            _check(load().asvd_svd_sigma(self.workspace.data_ptr(), self.m, self.n, self.batch, b, out.data_ptr(), _stream()))
         return out
 
     def extract(self, r: int, sigma_fuse: str = "UV", dtype: torch.dtype = torch.float16, b: int = 0):
@@ -144,8 +146,9 @@ class Factorisation:
         dev = self.workspace.device
         A = torch.empty(self.m, r, dtype=dtype, device=dev)
         B = torch.empty(r, self.n, dtype=dtype, device=dev)
-        _check(load().asvd_svd_extract(self.workspace.data_ptr(), self.m, self.n, self.batch, b, r, FUSE[sigma_fuse],
-                                       dtype_code(dtype), A.data_ptr(), r, B.data_ptr(), self.n, _stream()))
+        with torch.cuda.device(dev):
+            _check(load().asvd_svd_extract(self.workspace.data_ptr(), self.m, self.n, self.batch, b, r, FUSE[sigma_fuse],
+                                           dtype_code(dtype), A.data_ptr(), r, B.data_ptr(), self.n, _stream()))
         return A, B
 
 
