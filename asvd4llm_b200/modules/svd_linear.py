@@ -68,6 +68,11 @@ class SVDLinear(nn.Module):
                                  alpha=alpha, sigma_fuse=sigma_fuse, rank_align=rank_align)[0]
 
     def forward(self, inp):
+        if self.truncation_rank == 0:
+            # upstream quirk: a ratio so small that the rank formula gives 0 yields empty factors (svd_lowrank(q=0)
+            # succeeds), and ALinear(BLinear(x)) is the bias alone (zeros without one).  Nothing to contract.
+            y = inp.new_zeros(*inp.shape[:-1], self.ALinear.out_features)
+            return y if self.ALinear.bias is None else y + self.ALinear.bias
         # y = (x B^T) A^T + b in one C-ABI call (asvd_lowrank_forward)
         return _lib.lowrank_forward(inp, self.ALinear.weight, self.BLinear.weight, self.ALinear.bias)
 
@@ -148,8 +153,14 @@ def from_linear_batch(linears: Sequence[nn.Linear], param_ratios: Sequence[float
     assert len(linears) == len(param_ratios) and len(linears) > 0
     m, n = linears[0].out_features, linears[0].in_features
     ranks = [min(_lib.rank_for_ratio(m, n, pr, rank_align), min(m, n)) for pr in param_ratios]
-    if min(ranks) <= 0:
-        raise ValueError(f"param_ratio too small for a {m}x{n} layer: rank {min(ranks)}")
+    ranks = [max(r, 0) for r in ranks]
+    if max(ranks) == 0:
+        # rank 0 for every layer of the batch (upstream returns an SVDLinear with empty factors): no SVD to run
+        out = []
+        for lin in linears:
+            w = lin.weight.data
+            out.append(SVDLinear._from_factors(w.new_empty(m, 0), w.new_empty(0, n), lin.bias.data if lin.bias is not None else None))
+        return out
     fact = None
     if len(linears) == 1:
         key = _key(linears[0], act_aware, alpha)
@@ -167,6 +178,9 @@ def from_linear_batch(linears: Sequence[nn.Linear], param_ratios: Sequence[float
             out.append(_fallback(lin))
             continue
         w = lin.weight.data
+        if r == 0:
+            out.append(SVDLinear._from_factors(w.new_empty(m, 0), w.new_empty(0, n), lin.bias.data if lin.bias is not None else None))
+            continue
         A, B = fact.extract(r, sigma_fuse, w.dtype, b)
         if A.device != w.device:
             if w.device.type == "cpu":

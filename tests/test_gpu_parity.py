@@ -511,3 +511,48 @@ def test_layers_on_two_devices_in_one_process():
         outs.append((mod.ALinear.weight.data.cpu(), mod.BLinear.weight.data.cpu(), y.cpu(), acc.cpu()))
     for a, b in zip(outs[0], outs[1]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("m,n", [(1, 1), (1, 5), (5, 1), (2, 3), (7, 13), (13, 7), (65, 129), (129, 65), (127, 128), (1, 300), (300, 1)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_tiny_and_odd_shapes(m, n, dtype):
+    """Shapes far below one 64-vector block, odd, and degenerate (a single row / column), scaled: sigma against
+    torch.linalg.svd in fp64 and an exact reconstruction at full rank; a truncated extraction stays finite."""
+    L = _lib()
+    g = torch.Generator().manual_seed(1000 * m + n)
+    W = (torch.randn(m, n, generator=g) * 0.05).to(dtype)
+    s = (torch.rand(n, generator=g) + 0.25).float()
+    fact = L.scaled_svd([W.cuda()], [s.cuda()])
+    assert fact.status == 0
+    k = min(m, n)
+    S = torch.linalg.svdvals(W.double() * s.double())
+    sig = fact.sigma(0).cpu().double()
+    assert sig.shape == (k,) and torch.all(sig[:-1] >= sig[1:])
+    assert ((sig - S).abs() / (S + 1e-2 * S[0])).max().item() < SIGMA_RTOL
+    for fuse in ("UV", "U", "V"):
+        A, B = fact.extract(k, fuse, torch.float32)
+        rec = (A.cpu().double() @ B.cpu().double() - W.double()).norm() / W.double().norm()
+        assert rec < 1e-5, (fuse, rec)
+    if k > 1:
+        A, B = fact.extract(k - 1, "UV", dtype)
+        assert A.shape == (m, k - 1) and B.shape == (k - 1, n) and torch.isfinite(A).all() and torch.isfinite(B).all()
+        err = (A.double().cpu() @ B.double().cpu() - W.double()) * s.double()
+        # Eckart-Young: dropping the smallest singular value leaves exactly sigma_k (plus factor rounding in fp16)
+        assert abs(err.norm().item() - S[-1].item()) < 2e-3 * S[0].item()
+
+
+def test_rank_zero_mirrors_upstream():
+    """A ratio so small that the rank formula (svd_linear.py:39-44) gives 0: upstream returns an SVDLinear with empty
+    factors whose forward is the bias alone (probe on the upstream code: type SVDLinear, truncation_rank 0)."""
+    from asvd4llm_b200 import SVDLinear
+    lin = nn.Linear(64, 48).half().cuda()
+    mod = SVDLinear.from_linear(lin, 0.001)
+    assert isinstance(mod, SVDLinear) and mod.truncation_rank == 0
+    assert mod.ALinear.weight.shape == (48, 0) and mod.BLinear.weight.shape == (0, 64)
+    assert list(mod.state_dict().keys()) == ["ALinear.weight", "ALinear.bias", "BLinear.weight"]
+    x = torch.randn(2, 5, 64, device="cuda").half()
+    y = mod(x)
+    assert y.shape == (2, 5, 48) and torch.equal(y, lin.bias.data.expand(2, 5, 48))
+    lin2 = nn.Linear(64, 48, bias=False).half().cuda()
+    y2 = SVDLinear.from_linear(lin2, 0.001)(x)
+    assert y2.shape == (2, 5, 48) and (y2 == 0).all()
