@@ -79,7 +79,8 @@ def gather_sensitivity(model: nn.Module, shard: Dict[str, Dict[float, float]]) -
 
 def broadcast_factors(model: nn.Module, owners: Dict[str, int], replaced: Iterable[str]) -> None:
     """After a sharded final pass every rank installs every decomposed layer: the owner broadcasts
-    (rank r, ALinear.weight, BLinear.weight); bias tensors are already replicated."""
+    (rank r, ALinear.weight, BLinear.weight); bias tensors are already replicated.  A layer whose factorisation
+    failed on its owner is replicated as the plain nn.Linear the owner ended up with."""
     from .modules.svd_linear import SVDLinear
     rank, world = _world()
     if world == 1:
@@ -89,12 +90,29 @@ def broadcast_factors(model: nn.Module, owners: Dict[str, int], replaced: Iterab
     for full in replaced:
         src = owners[full]
         mod = by_name[full]
-        if rank == src:
-            meta = torch.tensor([mod.truncation_rank], dtype=torch.int64, device=mod.ALinear.weight.device)
-        else:
-            meta = torch.zeros(1, dtype=torch.int64, device=mod.weight.device)
+        is_svd = isinstance(mod, SVDLinear)
+        dev = (mod.ALinear.weight if is_svd else mod.weight).device
+        # rank -1: the owner's factorisation took upstream's failure path (svd_linear.py:66-68,80-98) and left a plain
+        # nn.Linear (fresh, or the raw layer with ASVD_B200_KEEP_RAW_ON_FAILURE=1); its weight and bias are
+        # replicated instead, so that every rank still holds the same model
+        meta = torch.tensor([(mod.truncation_rank if is_svd else -1) if rank == src else 0], dtype=torch.int64, device=dev)
         dist.broadcast(meta, src=src)
         r = int(meta.item())
+        if r < 0:
+            dist.broadcast(mod.weight.data, src=src)
+            if mod.bias is None:
+                # upstream's fallback layer always has a bias (nn.Linear default); receivers need the tensor first
+                has = torch.tensor([0], dtype=torch.int64, device=dev)
+            else:
+                has = torch.tensor([1], dtype=torch.int64, device=dev)
+            dist.broadcast(has, src=src)
+            if int(has.item()):
+                if mod.bias is None:
+                    mod.bias = nn.Parameter(torch.zeros(mod.out_features, dtype=mod.weight.dtype, device=dev))
+                dist.broadcast(mod.bias.data, src=src)
+            elif mod.bias is not None:
+                mod.bias = None
+            continue
         if rank == src:
             A, B = mod.ALinear.weight.data, mod.BLinear.weight.data
         else:

@@ -65,7 +65,20 @@ def _worker(rank, world, port, q):
                 ex = O.factorise_exact(lin.weight.data, 0.6, sdm=lin.scaling_diag_matrix, alpha=0.5, act_aware=True)
                 bias = lin.bias.data if lin.bias is not None else None
                 setattr(father, name, SVDLinear._from_factors(ex["A"], ex["B"], bias))
+        # one more layer whose factorisation "failed" on its owner: upstream's fallback is a fresh random nn.Linear
+        failed = list(full.keys())[5]
+        chosen[failed] = 0.6
+        if owners[failed] == rank:
+            father, name = next((f, n) for f, n, fn, _ in enumerate_linears(model) if fn == failed)
+            old_lin = getattr(father, name)
+            torch.manual_seed(1234 + rank)
+            setattr(father, name, nn.Linear(old_lin.in_features, old_lin.out_features))
         sharding.broadcast_factors(model, owners, list(chosen.keys()))
+        fl = dict(model.named_modules())[failed]
+        assert isinstance(fl, nn.Linear)
+        fdig = [None] * world
+        dist.all_gather_object(fdig, (float(fl.weight.double().sum()), float(fl.bias.double().sum())))
+        assert fdig[0] == fdig[1]
         sd = model.state_dict()
         digest = {k: float(v.double().sum()) for k, v in sd.items() if "ALinear" in k or "BLinear" in k}
         gathered = [None] * world
