@@ -111,7 +111,7 @@ def decompose_layers(model, chosen, default_ratio, args, layer_filter=None, batc
             mods = from_linear_batch([raw for _, _, raw in part], [ratio for _, ratio, _ in part], alpha=args.alpha,
                                      act_aware=args.act_aware, sigma_fuse=args.sigma_fuse, rank_align=args.rank_align)
             for (layer, _, raw), mod in zip(part, mods):
-                if uses[id(raw.weight)] <= 1:
+                if mod is not raw and uses[id(raw.weight)] <= 1:   # (ASVD_B200_KEEP_RAW_ON_FAILURE re-installs `raw` itself)
                     raw.to("cpu")                               # upstream frees the replaced weight (:127)
                 father, name = where[raw]
                 setattr(father, name, mod)
