@@ -1285,6 +1285,8 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
   float tol_pre = pre_env ? (float)atof(pre_env) : 5.f * tol;
   if (conv_tol > 0.f) tol_pre = conv_tol;          // experiments (ASVD_B200_INNER_TOL): looser tolerance for the square stage
   if (tol_pre < tol) tol_pre = tol;
+  const char* near_env = getenv("ASVD_B200_NEAR_PCT");
+  const unsigned near_min = near_env ? (unsigned)(atof(near_env) * 0.01 * p.rounds * p.pairs) : 0u;
   std::vector<unsigned> h_maxoff(2 * (size_t)p.batch);
   std::vector<int> h_done(p.batch, 0), h_sweeps(p.batch, 0);
   bool gave_up = false;
@@ -1378,7 +1380,9 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
       }
       if (finished) { h_done[b] = 1; changed = true; }
       else { all_done = false; worst = fmaxf(worst, mo); best = fminf(best, mo); }
-      if (h_maxoff[near_idx(b)] > 0) near_seen = true;
+      // ASVD_B200_NEAR_PCT (experiments): stay with the single-pass Gram until that percentage of a matrix's block pairs
+      // is below 1e-2 (default 0: the first such pair switches to the precise Gram)
+      if (h_maxoff[near_idx(b)] > near_min) near_seen = true;
     }
     (void)worst; (void)best;
     if (getenv("ASVD_B200_TRACE")) {                 // diagnostic: convergence trace, one line per sweep
