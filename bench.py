@@ -101,6 +101,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle import asvd_oracle as O
+    torch.set_num_threads(_host_threads())             # torchrun exports OMP_NUM_THREADS=1; this arm uses every host thread
     torch.manual_seed(233)
     lin = make_cpu_linear(233)
     for _ in range(max(1, min(args.warmup, 1))):       # one warm-up is enough for a CPU LAPACK path
@@ -112,7 +113,7 @@ def run_reference(args, rank, world):
     value = args.steps / dt
     cores = torch.get_num_threads()
     sample = f"{args.steps} x one 4096x4096 fp16 weight @0.9 per step (scale, svd_lowrank q=1843 niter=2, un-scale, fuse, cast)"
-    print(json.dumps({
+    _emit(({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -123,7 +124,39 @@ def run_reference(args, rank, world):
     }))
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """Rank 0 prints ONE JSON line on stdout.  Libraries write there too (NCCL's version banner comes through C stdio
+    whatever NCCL_DEBUG_FILE says), so file descriptor 1 is pointed at stderr for the run and the JSON line goes to
+    the saved descriptor."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
+def _host_threads() -> int:
+    """All the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers, which would make
+    the CPU arm single-threaded at N > 1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -315,6 +348,7 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import asvd_oracle as O
+        torch.set_num_threads(_host_threads())
         torch.manual_seed(233)
         lin = make_cpu_linear(233)
         reference_step(lin, O)
@@ -325,7 +359,7 @@ def main():
                         "sample": "3 x one 4096x4096 fp16 weight @0.9 (scale, svd_lowrank q=1843 niter=2, un-scale, fuse, cast), median"}
 
     if rank == 0:
-        print(json.dumps({
+        _emit(({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
