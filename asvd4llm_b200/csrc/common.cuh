@@ -98,6 +98,9 @@ __device__ __forceinline__ bool pair_is_clean(const int* __restrict__ track, int
   return t[nb + I * nb + J] >= max(t[I], t[J]);
 }
 
+// floats per block pair of the lean solve's global record (svd_solve_quad.cuh: QAUX_FLOATS, checked there)
+constexpr size_t QAUX_FLOATS_PLAN = 127 * 128 + 3 * 128 + 128 + 128;
+
 struct SvdPlan {
   int m, n, batch;
   int tall;        // 1: m >= n, vectors are columns of W*s (length m); 0: vectors are rows (length n)
@@ -108,7 +111,7 @@ struct SvdPlan {
   int nb, rounds, pairs, chunks, chunk_cols;
   // byte offsets into the workspace
   size_t off_ptrs, off_pairs, off_X, off_Xr, off_Y, off_G, off_R, off_flag, off_maxoff, off_done, off_sigma, off_perm,
-      off_status, off_scale, off_norm, off_track, off_As, off_Bs, off_Yp, off_Gm, off_inner;
+      off_status, off_scale, off_norm, off_track, off_As, off_Bs, off_Yp, off_Gm, off_inner, off_aux;
   int gram_pre;    // 1: rectangular enough for the Gram pre-conditioner (workspace holds the inner square problem)
   size_t bytes;
 };

@@ -152,6 +152,8 @@ SvdPlan make_plan(int m, int n, int batch, bool allow_inner) {
     p.off_Gm = take(sizeof(float) * (size_t)batch * p.nv_pad * p.nv_pad);
     p.off_inner = take(make_plan(p.nv, p.nv, batch, false).bytes);
   }
+  // per-pair record of the lean solve (ASVD_B200_SOLVE=lean): rotation history, scales, column order (svd_solve_quad.cuh)
+  p.off_aux = take(sizeof(float) * (size_t)batch * p.pairs * QAUX_FLOATS_PLAN);
   p.bytes = off;
   return p;
 }
@@ -361,6 +363,7 @@ __device__ __forceinline__ float2 jacobi_scaled(float ghat_pp, float ghat_qq, fl
 // Common head of the solve kernels: G = sum of the partial Grams into shared memory, convergence measure of the
 // pair at visit time, non-finite check, threshold test and clean-pair bookkeeping.  Returns false when the CTA has
 // nothing to rotate.
+template <int NT = SOLVE_THREADS>
 __device__ __forceinline__ bool solve_prologue(const float* __restrict__ Gpart, int chunks, int idx, int b, int2 pr, int tid,
                                                float* G, float* red, int* __restrict__ pairflag,
                                                unsigned* __restrict__ maxoff_bits, int* __restrict__ status, float tol,
@@ -370,44 +373,66 @@ __device__ __forceinline__ bool solve_prologue(const float* __restrict__ Gpart, 
   {
     // G = sum of the partial Grams.  16384 elements over 512 threads = 8 float4 per thread and chunk; all loads of
     // a chunk are issued before the first add so ~32 KB per warp are in flight
+    // (NT threads: JK*JK/4/NT float4 per thread, in passes of 8 so that a 256-thread CTA stays within its registers;
+    // every element still sums its chunks in the same order, whatever NT)
     const float4* Gp4 = reinterpret_cast<const float4*>(Gp);
-    float4 acc[8];
+#pragma unroll 1
+    for (int pass = 0; pass < JK * JK / 4 / NT / 8; ++pass) {
+      const int base = tid + NT * 8 * pass;
+      float4 acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int c = 0; c < chunks; ++c) {
-      float4 v[8];
+      for (int i = 0; i < 8; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < chunks; ++c) {
+        float4 v[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = Gp4[(int64_t)c * (JK * JK / 4) + tid + SOLVE_THREADS * i];
+        for (int i = 0; i < 8; ++i) v[i] = Gp4[(int64_t)c * (JK * JK / 4) + base + NT * i];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { acc[i].x += v[i].x; acc[i].y += v[i].y; acc[i].z += v[i].z; acc[i].w += v[i].w; }
-    }
+        for (int i = 0; i < 8; ++i) { acc[i].x += v[i].x; acc[i].y += v[i].y; acc[i].z += v[i].z; acc[i].w += v[i].w; }
+      }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int e = (tid + SOLVE_THREADS * i) * 4;
-      *reinterpret_cast<float4*>(&G[(e >> 7) * SLD + (e & (JK - 1))]) = acc[i];
+      for (int i = 0; i < 8; ++i) {
+        const int e = (base + NT * i) * 4;
+        *reinterpret_cast<float4*>(&G[(e >> 7) * SLD + (e & (JK - 1))]) = acc[i];
+      }
     }
   }
   __syncthreads();
   if (half_gram) {
     // the tensor-core Gram pass in precise mode delivers T = (0.5 HI + LO) HI^T; the Gram matrix is T + T^T
-    float v[32];
+    if constexpr (NT == SOLVE_THREADS) {
+      constexpr int PER = JK * JK / NT;
+      float v[PER];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const int e = tid + SOLVE_THREADS * k, r = e >> 7, c = e & (JK - 1);
-      v[k] = G[r * SLD + c] + G[c * SLD + r];
-    }
-    __syncthreads();
+      for (int k = 0; k < PER; ++k) {
+        const int e = tid + NT * k, r = e >> 7, c = e & (JK - 1);
+        v[k] = G[r * SLD + c] + G[c * SLD + r];
+      }
+      __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const int e = tid + SOLVE_THREADS * k;
-      G[(e >> 7) * SLD + (e & (JK - 1))] = v[k];
+      for (int k = 0; k < PER; ++k) {
+        const int e = tid + NT * k;
+        G[(e >> 7) * SLD + (e & (JK - 1))] = v[k];
+      }
+    } else {
+      // fewer threads: in place, the thread that owns (r, c) with r < c also writes (c, r); the sum is the same
+      // floating-point value either way round, so the result equals the staged version bit for bit
+#pragma unroll 4
+      for (int e = tid; e < JK * JK; e += NT) {
+        const int r = e >> 7, c = e & (JK - 1);
+        if (r < c) {
+          const float v = G[r * SLD + c] + G[c * SLD + r];
+          G[r * SLD + c] = v; G[c * SLD + r] = v;
+        } else if (r == c) {
+          G[r * SLD + r] += G[r * SLD + r];
+        }
+      }
     }
     __syncthreads();
   }
   // convergence measure of this pair at visit time: max |cos| between any two of its 128 vectors
   float mx = 0.f;
   int bad = 0;
-  for (int e = tid; e < JK * JK; e += SOLVE_THREADS) {
+  for (int e = tid; e < JK * JK; e += NT) {
     int r = e >> 7, c = e & (JK - 1);
     float g = G[r * SLD + c];
     if (!(fabsf(g) <= FLT_MAX)) bad = 1;
@@ -421,8 +446,8 @@ __device__ __forceinline__ bool solve_prologue(const float* __restrict__ Gpart, 
   if ((tid & 31) == 0) { red[tid >> 5] = mx; red[32 + (tid >> 5)] = bad ? 1.f : 0.f; }
   __syncthreads();
   if (tid < 32) {
-    float v = warp_max(tid < SOLVE_THREADS / 32 ? red[tid] : 0.f);
-    float bb = warp_max(tid < SOLVE_THREADS / 32 ? red[32 + tid] : 0.f);
+    float v = warp_max(tid < NT / 32 ? red[tid] : 0.f);
+    float bb = warp_max(tid < NT / 32 ? red[32 + tid] : 0.f);
     if (tid == 0) { red[0] = v; red[32] = bb; }
   }
   __syncthreads();
@@ -1174,6 +1199,9 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
   if (!attrs_set) {
     ASVD_CUDA_CHECK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
     ASVD_CUDA_CHECK(cudaFuncSetAttribute(solve_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVEQ_SMEM));
+    ASVD_CUDA_CHECK(cudaFuncSetAttribute(solve_quad_g_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVEQG_SMEM));
+    ASVD_CUDA_CHECK(cudaFuncSetAttribute(solve_quad_g_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   // two CTAs per SM
+    ASVD_CUDA_CHECK(cudaFuncSetAttribute(solve_quad_r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVEQR_SMEM));
     ASVD_CUDA_CHECK(upload_quad_schedule());
     ASVD_CUDA_CHECK(cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPDATE_SMEM));
     ASVD_CUDA_CHECK(cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 16384));
@@ -1221,7 +1249,10 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
   // Measured: the quad ordering needs about half a sweep more than the odd-even one.  On square problems its faster
   // step wins (-6% wall clock); on 2.7:1 rectangles, where the streaming passes dominate a round, it loses 3%.
   const bool quad_pays = p.len_pad < 2 * p.nv_pad;
-  const bool solve_quad = !dbg_env && (solve_env ? solve_env[0] == 'q' : quad_pays);
+  // ASVD_B200_SOLVE=lean (experimental, see svd_solve_quad.cuh): G-only sweep at two CTAs per SM + R replay kernel;
+  // default tail only
+  const bool solve_lean = !dbg_env && solve_env && solve_env[0] == 'l' && polish_flag == 2;
+  const bool solve_quad = !dbg_env && !solve_lean && (solve_env ? solve_env[0] == 'q' : quad_pays);
   const char* simt_env = getenv("ASVD_B200_SIMT");
   const bool use_tc = !(simt_env && simt_env[0] == '1');
   // Overlapped half-batches (ASVD_B200_OVERLAP=1).  The solve is a chain of 127 dependent rotation steps on one CTA per
@@ -1326,7 +1357,11 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
         }
         // the token: this half's solve starts when the other half's latest solve has finished
         if (n_parts == 2 && !(r == 0 && h == 0)) ASVD_CUDA_CHECK(cudaStreamWaitEvent(s, ev_solve[h ^ 1], 0));
-        if (solve_quad)
+        if (solve_lean) {
+          float* auxq = reinterpret_cast<float*>(ws + p.off_aux) + (size_t)q.b0 * p.pairs * QAUX_FLOATS;
+          ASVD_LAUNCH(K_SOLVE, s, (solve_quad_g_kernel<<<dim3(p.pairs, q.nb), 256, SOLVEQG_SMEM, s>>>(Gq, p.chunks, p.pairs, auxq, flagq, maxoffq, statusq, doneq, tol, pr, trackq, p.nb, round_stamp, gram_precise, half_gram)));
+          ASVD_LAUNCH(K_SOLVE, s, (solve_quad_r_kernel<<<dim3(p.pairs, q.nb), 256, SOLVEQR_SMEM, s>>>(auxq, p.pairs, Rq, flagq, doneq)));
+        } else if (solve_quad)
           ASVD_LAUNCH(K_SOLVE, s, (solve_quad_kernel<<<dim3(p.pairs, q.nb), SOLVE_THREADS, SOLVEQ_SMEM, s>>>(Gq, p.chunks, p.pairs, Rq, flagq, maxoffq, statusq, doneq, tol, polish_flag, pr, trackq, p.nb, round_stamp, gram_precise, half_gram)));
         else
           ASVD_LAUNCH(K_SOLVE, s, (solve_kernel<<<dim3(p.pairs, q.nb), SOLVE_THREADS, SOLVE_SMEM, s>>>(Gq, p.chunks, p.pairs, Rq, flagq, maxoffq, statusq, doneq, tol, polish_flag, dbg_steps, pr, trackq, p.nb, round_stamp, gram_precise, half_gram)));

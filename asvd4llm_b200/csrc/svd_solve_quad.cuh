@@ -96,9 +96,10 @@ __device__ __forceinline__ void load_q4(const float2* src, float2 (&q)[4]) {
 // computes the four rotations of every group from its registers, publishes them and only ARRIVES at the step's named
 // barrier, so it runs ahead of the other seven warps (which wait on that barrier) by up to a whole round; the barrier
 // ids of a round are distinct and the blocking barriers of the quad move separate their reuse.
-template <int TYPE>
+template <int TYPE, bool LEAN = false>
 __device__ __forceinline__ void quad_g_step(float (&g)[8][8], float (&d)[8], bool lead, bool is_diag, float2* cs_step, int pa,
-                                            int pc, int gtid, uint64_t* mb, int step, int bar_id) {
+                                            int pc, int gtid, uint64_t* mb, int step, int bar_id,
+                                            float2* __restrict__ hist_step = nullptr) {
   if (lead) {
     // The parameter arithmetic is the dependent chain of the whole sweep (~35 instructions per pivot at ~4 cycles
     // each for a single warp), so it is spread over all 32 lanes: diagonal lane L keeps pivots 0 and 1 and hands
@@ -135,10 +136,14 @@ __device__ __forceinline__ void quad_g_step(float (&g)[8][8], float (&d)[8], boo
       }
       *reinterpret_cast<float4*>(cs_step + 4 * pa) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
       *reinterpret_cast<float4*>(cs_step + 4 * pa + 2) = make_float4(back[0].x, back[0].y, back[1].x, back[1].y);
+      if (LEAN) {                                          // the replay kernel reads the rotations from HBM / L2
+        *reinterpret_cast<float4*>(hist_step + 4 * pa) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+        *reinterpret_cast<float4*>(hist_step + 4 * pa + 2) = make_float4(back[0].x, back[0].y, back[1].x, back[1].y);
+      }
     }
     __syncwarp();
     asm volatile("bar.arrive %0, 256;" ::"r"(bar_id) : "memory");
-    if (gtid == 0) tc::mbar_arrive(&mb[step]);             // release: the R threads may consume this step
+    if (!LEAN && gtid == 0) tc::mbar_arrive(&mb[step]);    // release: the R threads may consume this step
   } else {
     asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
   }
@@ -149,9 +154,9 @@ __device__ __forceinline__ void quad_g_step(float (&g)[8][8], float (&d)[8], boo
   quad_cols<TYPE>(g, qc);
 }
 
-template <int TYPE>
+template <int TYPE, bool WAIT = true>
 __device__ __forceinline__ void quad_r_step(float (&r)[8][8], const float2* cs_step, int pc, uint64_t* mb, int step) {
-  tc::mbar_wait(&mb[step], 0);                             // acquire; every barrier of the array is used once
+  if (WAIT) tc::mbar_wait(&mb[step], 0);                   // acquire; every barrier of the array is used once
   float2 qc[4];
   load_q4(cs_step + 4 * pc, qc);
   quad_cols<TYPE>(r, qc);
@@ -428,4 +433,239 @@ solve_quad_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat
   }
   __syncthreads();
   solve_polish_write(G, Rs, Rout, idx, tid, transpose_out);
+}
+
+
+// ================================================================================================ lean variant
+// EXPERIMENTAL (ASVD_B200_SOLVE=lean; written at the end of round 1 without GPU time left: compiled, not yet run).
+// Why.  solve_quad_kernel is 512 threads x 128 registers: it fills an SM's register file, so a batch of four 4096^2
+// occupies 128 SMs for 120 us at 27 % issue utilisation, and no other work can share those SMs (levers).
+// Half of its threads only accumulate R and follow the G threads through the 65 KB rotation history.  Here the sweep is
+// split in two kernels:
+//   solve_quad_g_kernel  the 256 G threads alone: same steps, same barriers, same arithmetic; the lead warp ALSO
+//                        streams every step's 64 rotations (512 B) to a global history and the history in shared
+//                        memory shrinks to a ring of 8 steps (the lead warp is never more than 7 steps ahead: the
+//                        quad move at the end of a round is a blocking barrier).  256 threads x 128 registers and
+//                        ~75 KB of shared memory: TWO CTAs per SM, i.e. 296 block pairs in one wave.
+//   solve_quad_r_kernel  replays the complete history on R (the R half of solve_quad_kernel without the mbarrier
+//                        waits: throughput-bound, no dependent chain), sorts, normalises and writes R.
+// Same operations in the same order on every element: R is expected to be bitwise the one solve_quad_kernel writes.
+constexpr int QRING = 8;
+// per-pair global record: rotation history, folded scales, final scales, output column of every position
+constexpr size_t QAUX_FLOATS = (size_t)QSTEPS * 128 + (size_t)QFOLDS * JK + JK + JK;
+static_assert(QAUX_FLOATS == QAUX_FLOATS_PLAN && QAUX_FLOATS % 4 == 0, "workspace plan and lean solve record disagree");
+constexpr size_t SOLVEQG_SMEM = sizeof(float) * (JK * SLD) + sizeof(float2) * QRING * 64 + sizeof(float) * 64 +
+                                sizeof(float) * JK * 3 + (QROUNDS - 1) * 32;
+constexpr size_t SOLVEQR_SMEM = sizeof(float) * (JK * SLD) + sizeof(float2) * QSTEPS * 64 + sizeof(float) * JK * (QFOLDS + 1) +
+                                sizeof(int) * JK + (QROUNDS - 1) * 32;
+
+__global__ void __launch_bounds__(256, 2)
+solve_quad_g_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, float* __restrict__ aux,
+                    int* __restrict__ pairflag, unsigned* __restrict__ maxoff_bits, int* __restrict__ status,
+                    const int* __restrict__ done, float tol, const int2* __restrict__ pairs, int* __restrict__ track, int nb,
+                    int round_stamp, int precise, int half_gram) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* G = reinterpret_cast<float*>(smem_raw);            // [JK][SLD] summed Gram, then the staging area of the moves
+  float2* csh = reinterpret_cast<float2*>(G + JK * SLD);    // [QRING][64] rotations of the last steps
+  float* red = reinterpret_cast<float*>(csh + QRING * 64);  // [64]
+  float* gd = red + 64;                                     // [JK] final diagonal (true norms)
+  float* dmov = gd + JK;                                    // [JK] scales in transit during a quad move
+  float* dfold = dmov + JK;                                 // [JK] scales being folded into G
+  unsigned char* qsrc = reinterpret_cast<unsigned char*>(dfold + JK);
+
+  const int b = blockIdx.y, p = blockIdx.x;
+  if (done[b]) return;
+  const int idx = b * pairs_per_mat + p;
+  const int tid = threadIdx.x;
+  const int2 pr = pairs[p];
+  int* trk = track + (int64_t)b * (nb + nb * nb);
+  if (pair_is_clean(track, nb, b, pr.x, pr.y)) {
+    if (tid == 0) pairflag[idx] = 0;
+    return;
+  }
+  for (int i = tid; i < (QROUNDS - 1) * 32; i += 256) qsrc[i] = c_quad_src[i];
+  if (!solve_prologue<256>(Gpart, chunks, idx, b, pr, tid, G, red, pairflag, maxoff_bits, status, tol, trk, nb, round_stamp,
+                           precise, gridDim.y, half_gram))
+    return;
+
+  float* ax = aux + (int64_t)idx * QAUX_FLOATS;
+  float2* hist = reinterpret_cast<float2*>(ax);             // [QSTEPS][64]
+  float* a_dhist = ax + (size_t)QSTEPS * 128;               // [QFOLDS][JK]
+  float* a_dfin = a_dhist + QFOLDS * JK;                    // [JK]
+  int* a_dest = reinterpret_cast<int*>(a_dfin + JK);        // [JK]
+
+  const int lt = tid;
+  const int pa = lt & 15, pc = (pa + (lt >> 4)) & 15;
+  float g[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 x0 = *reinterpret_cast<const float4*>(&G[(8 * pa + i) * SLD + 8 * pc]);
+    const float4 x1 = *reinterpret_cast<const float4*>(&G[(8 * pa + i) * SLD + 8 * pc + 4]);
+    g[i][0] = x0.x; g[i][1] = x0.y; g[i][2] = x0.z; g[i][3] = x0.w;
+    g[i][4] = x1.x; g[i][5] = x1.y; g[i][6] = x1.z; g[i][7] = x1.w;
+  }
+  float d[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) d[i] = 1.f;
+  const bool is_diag = (pa == pc);
+  const bool lead = lt < 32;
+  auto bar_g = [] { asm volatile("bar.sync 2, 256;" ::: "memory"); };
+  bar_g();                                                  // every patch is in registers: G becomes the staging area
+
+#define QG_STEP(TYPE, S, BAR) \
+  quad_g_step<TYPE, true>(g, d, lead, is_diag, csh + ((S) & (QRING - 1)) * 64, pa, pc, lt, nullptr, (S), (BAR), hist + (S) * 64)
+  QG_STEP(0, 0, 8);
+  QG_STEP(1, 1, 9);
+  QG_STEP(2, 2, 10);
+#pragma unroll 1
+  for (int r = 0; r < QROUNDS; ++r) {
+    const int s0 = 3 + 4 * r;
+    QG_STEP(3, s0 + 0, 4);
+    QG_STEP(4, s0 + 1, 5);
+    QG_STEP(5, s0 + 2, 6);
+    QG_STEP(6, s0 + 3, 7);
+    if (r == QROUNDS - 1) break;
+    if ((r & 7) == 7) {
+      // fold the deferred scales back into the stored values; the replay kernel folds the same values into R
+      if (is_diag) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { dfold[8 * pa + i] = d[i]; a_dhist[(r >> 3) * JK + 8 * pa + i] = d[i]; d[i] = 1.f; }
+      }
+      bar_g();
+      float dr[8], dc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { dr[i] = dfold[8 * pa + i]; dc[i] = dfold[8 * pc + i]; }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[i][j] *= dr[i] * dc[j];
+      // (dfold is next written eight rounds later, behind many blocking barriers)
+    }
+    const unsigned char* qs = qsrc + r * 32;
+    const int rsrcL = qs[2 * pa], rsrcH = qs[2 * pa + 1], csrcL = qs[2 * pc], csrcH = qs[2 * pc + 1];
+    const bool mrL = rsrcL != 8 * pa, mrH = rsrcH != 8 * pa + 4, mcL = csrcL != 8 * pc, mcH = csrcH != 8 * pc + 4;
+    const bool mv[4] = {mrL || mcL, mrL || mcH, mrH || mcL, mrH || mcH};
+    quad_stage_write(G, g, pa, pc, mv);
+    if (is_diag) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dmov[8 * pa + i] = d[i];
+    }
+    bar_g();
+    quad_stage_read(G, g, rsrcL, rsrcH, csrcL, csrcH, mv);
+    if (is_diag) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] = dmov[(i < 4 ? rsrcL : rsrcH) + (i & 3)];
+    }
+    bar_g();
+  }
+#undef QG_STEP
+  if (is_diag) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { gd[8 * pa + i] = d[i] * d[i] * g[i][i]; a_dfin[8 * pa + i] = d[i]; }
+  }
+  bar_g();
+  if (lt < JK) {
+    const float dd = gd[lt];
+    int rank = 0;
+    for (int j = 0; j < JK; ++j) {
+      const float e = gd[j];
+      rank += (e > dd) || (e == dd && j < lt);
+    }
+    a_dest[lt] = rank;
+  }
+}
+
+__global__ void __launch_bounds__(256, 1)
+solve_quad_r_kernel(const float* __restrict__ aux, int pairs_per_mat, float* __restrict__ Rout,
+                    const int* __restrict__ pairflag, const int* __restrict__ done) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* Rs = reinterpret_cast<float*>(smem_raw);           // [JK][SLD] staging of the moves; then R, sorted columns
+  float2* csh = reinterpret_cast<float2*>(Rs + JK * SLD);   // [QSTEPS][64] the complete rotation history
+  float* dhist = reinterpret_cast<float*>(csh + QSTEPS * 64);   // [QFOLDS][JK]
+  float* dfin = dhist + QFOLDS * JK;                        // [JK]
+  int* dest = reinterpret_cast<int*>(dfin + JK);            // [JK]
+  unsigned char* qsrc = reinterpret_cast<unsigned char*>(dest + JK);
+  __shared__ float cnp[4][JK];
+
+  const int b = blockIdx.y, p = blockIdx.x;
+  if (done[b]) return;
+  const int idx = b * pairs_per_mat + p;
+  if (!pairflag[idx]) return;                               // clean, converged or non-finite pair: no rotation, no R
+  const int tid = threadIdx.x;
+  const float* ax = aux + (int64_t)idx * QAUX_FLOATS;
+  {
+    // history, scales and destinations are one contiguous record: float4 copies (QAUX_FLOATS is a multiple of 4)
+    const float4* src = reinterpret_cast<const float4*>(ax);
+    float4* dst = reinterpret_cast<float4*>(csh);           // csh | dhist | dfin | dest are contiguous in shared memory too
+    for (int i = tid; i < (int)(QAUX_FLOATS / 4); i += 256) dst[i] = src[i];
+    for (int i = tid; i < (QROUNDS - 1) * 32; i += 256) qsrc[i] = c_quad_src[i];
+  }
+  __syncthreads();
+
+  const int pa = tid & 15, pc = (pa + (tid >> 4)) & 15;
+  float r[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[i][j] = (pa == pc && i == j) ? 1.f : 0.f;
+  quad_r_step<0, false>(r, csh + 0 * 64, pc, nullptr, 0);
+  quad_r_step<1, false>(r, csh + 1 * 64, pc, nullptr, 1);
+  quad_r_step<2, false>(r, csh + 2 * 64, pc, nullptr, 2);
+#pragma unroll 1
+  for (int rd = 0; rd < QROUNDS; ++rd) {
+    const int s0 = 3 + 4 * rd;
+    quad_r_step<3, false>(r, csh + (s0 + 0) * 64, pc, nullptr, s0 + 0);
+    quad_r_step<4, false>(r, csh + (s0 + 1) * 64, pc, nullptr, s0 + 1);
+    quad_r_step<5, false>(r, csh + (s0 + 2) * 64, pc, nullptr, s0 + 2);
+    quad_r_step<6, false>(r, csh + (s0 + 3) * 64, pc, nullptr, s0 + 3);
+    if (rd == QROUNDS - 1) break;
+    if ((rd & 7) == 7) {
+      const float* dh = dhist + (rd >> 3) * JK;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dc = dh[8 * pc + j];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i][j] *= dc;
+      }
+    }
+    const unsigned char* qs = qsrc + rd * 32;
+    const int csrcL = qs[2 * pc], csrcH = qs[2 * pc + 1];
+    const bool mcL = csrcL != 8 * pc, mcH = csrcH != 8 * pc + 4;
+    const bool mv[4] = {mcL, mcH, mcL, mcH};                // rows never move: only the column quads decide
+    quad_stage_write(Rs, r, pa, pc, mv);
+    __syncthreads();
+    quad_stage_read(Rs, r, 8 * pa, 8 * pa + 4, csrcL, csrcH, mv);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int col = dest[8 * pc + j];
+    const float dc = dfin[8 * pc + j];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) Rs[(8 * pa + i) * SLD + col] = r[i][j] * dc;
+  }
+  __syncthreads();
+  // unit column norms (the default tail of solve_polish_write, same partial sums in the same order), then store
+  {
+    const int col = tid & (JK - 1);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int part = (tid >> 7) + 2 * h;
+      float ss = 0.f;
+#pragma unroll 8
+      for (int l = 0; l < JK / 4; ++l) { const float x = Rs[(part * (JK / 4) + l) * SLD + col]; ss = fmaf(x, x, ss); }
+      cnp[part][col] = ss;
+    }
+  }
+  __syncthreads();
+  if (tid < JK) cnp[0][tid] = rsqrtf(cnp[0][tid] + cnp[1][tid] + cnp[2][tid] + cnp[3][tid]);
+  __syncthreads();
+  float* Ro = Rout + (int64_t)idx * (JK * JK);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int e = (tid + 256 * k) * 4, rr = e >> 7, c = e & (JK - 1);
+    const float4 x = *reinterpret_cast<const float4*>(&Rs[rr * SLD + c]);
+    const float4 n = *reinterpret_cast<const float4*>(&cnp[0][c]);
+    *reinterpret_cast<float4*>(&Ro[e]) = make_float4(x.x * n.x, x.y * n.y, x.z * n.z, x.w * n.w);
+  }
 }
