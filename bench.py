@@ -328,8 +328,11 @@ def main():
         if os.path.exists(tpath):
             traffic = json.load(open(tpath))
         per_kernel, t_round = {}, 0.0
+        # time of a class per ROUND (= per Gram launch; the quad solve is one launch per round, the experimental lean
+        # solve two)
+        rounds = max(1, classes["gram"]["launches"])
         for k in ("gram", "solve", "update"):
-            us = classes[k]["ms"] / classes[k]["launches"] * 1e3
+            us = classes[k]["ms"] / rounds * 1e3
             t_round += us
             per_kernel[k + "_kernel"] = {"avg_launch_us": round(us, 1), "algorithmic_bytes_per_launch": alg[k],
                                          "achieved_GBps": round(alg[k] / us / 1e3, 1), "frac_of_hbm_peak": round(alg[k] / us / 1e3 / peak, 3),
