@@ -11,6 +11,9 @@ g = torch.Generator(device=dev).manual_seed(1)
 sweeps = int(os.environ.get("SAN_SWEEPS", "3"))
 cases = [(512, 384, 2, "0"), (384, 640, 1, "0"), (2304, 1024, 1, "0"), (512, 512, 3, "1"), (640, 384, 2, "1"),
          (1, 5, 1, "0"), (5, 1, 1, "0"), (7, 13, 1, "0"), (129, 65, 2, "1"), (1, 300, 1, "0"), (300, 1, 1, "0")]
+if os.environ.get("SAN_LEAN") == "1":           # the experimental lean solve (racecheck it before it becomes a default)
+    os.environ["ASVD_B200_SOLVE"] = "lean"
+    cases = [(512, 512, 2, "0"), (384, 640, 1, "0"), (1024, 1024, 3, "1"), (129, 65, 2, "0")]
 for (m, n, B, overlap) in cases:
     os.environ["ASVD_B200_OVERLAP"] = overlap
     Ws = [(torch.randn(m, n, device=dev, generator=g) * 0.02).half() for _ in range(B)]
