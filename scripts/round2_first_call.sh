@@ -8,8 +8,8 @@ SAN_LEAN=1 SAN_SWEEPS=1 timeout 300 compute-sanitizer --tool racecheck --error-e
 # 2. timings, three repetitions: square at 4 / 8 / 9 with both solves
 AB_REPS=3 timeout 120 python scripts/ab_lean.py quad:4 quad:8 quad:9 lean:8 lean:9 lean:10 2>&1 | tee gpurun_out/r02_ab_lean.jsonl
 # 3. the Llama rectangles at one and two waves (Gram pre-conditioner inside), quad and lean
-for s in quad lean; do
-  ASVD_B200_SOLVE=$s timeout 120 python scripts/ab_overlap.py 11008x4096x4 11008x4096x8 4096x11008x4 4096x11008x8 2>&1 | tee gpurun_out/r02_rect_$s.jsonl
-done
+# (default = odd-even outer solve on 2.7:1 shapes, quad inside the pre-conditioner; lean forces the lean solve in both)
+timeout 120 python scripts/ab_overlap.py 11008x4096x4 11008x4096x8 4096x11008x4 4096x11008x8 2>&1 | tee gpurun_out/r02_rect_default.jsonl
+ASVD_B200_SOLVE=lean timeout 120 python scripts/ab_overlap.py 11008x4096x4 11008x4096x8 4096x11008x4 4096x11008x8 2>&1 | tee gpurun_out/r02_rect_lean.jsonl
 # 4. the bench as the driver runs it
 timeout 200 python bench.py > gpurun_out/r02_bench_1gpu.json 2> gpurun_out/r02_bench_1gpu.err; tail -c 500 gpurun_out/r02_bench_1gpu.json
