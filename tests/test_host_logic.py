@@ -69,3 +69,27 @@ def test_cache_file_names_match_upstream(golden_pipeline):
     got = {_cache_file(model, "abs_mean").split("/")[-1], _cache_file(model, "abs_max").split("/")[-1],
            sensitivity_cache_file(model, _args()).split("/")[-1]}
     assert got == set(golden_pipeline["sensitivity_cache_files"])
+
+
+def test_calibration_cache_files_are_read_without_a_gpu(golden_pipeline, tmp_path, monkeypatch):
+    """--use_cache: upstream's published cache files (README.md:110-114) are accepted as they are; reading them needs
+    no kernel.  Covers calib_input_distribution (act_aware_utils.py:49-60) and calib_fisher_info (:9-16)."""
+    import os
+    from conftest import GOLDEN
+    from asvd4llm_b200.act_aware_utils import calib_input_distribution, calib_fisher_info
+    fisher = torch.load(os.path.join(GOLDEN, "tiny_opt_fisher.pt"), weights_only=False)
+    monkeypatch.chdir(tmp_path); os.makedirs("cache")
+    torch.save(golden_pipeline["sdm_abs_mean"], "cache/synthetic_tiny-opt_calib_input_distribution_abs_mean.pt")
+    torch.save(fisher["fisher_info"], "cache/" + fisher["cache_files"][0])
+    model = build_tiny_opt(golden_pipeline)
+    calib_input_distribution(model, golden_pipeline["loader"], "abs_mean", use_cache=True)
+    calib_fisher_info(model, golden_pipeline["loader"], use_cache=True)
+    for name, mod in model.named_modules():
+        if isinstance(mod, nn.Linear):
+            assert torch.equal(mod.scaling_diag_matrix, golden_pipeline["sdm_abs_mean"][name])
+            assert torch.equal(mod.fisher_info, fisher["fisher_info"][name])
+    # without the cache the product needs its CUDA library and a device: it must fail loudly, not fall back
+    model2 = build_tiny_opt(golden_pipeline)
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception):
+            calib_input_distribution(model2, golden_pipeline["loader"], "abs_max", use_cache=False)
