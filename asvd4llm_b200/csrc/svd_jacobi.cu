@@ -1251,7 +1251,17 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
   const bool quad_pays = p.len_pad < 2 * p.nv_pad;
   // ASVD_B200_SOLVE=lean (experimental, see svd_solve_quad.cuh): G-only sweep at two CTAs per SM + R replay kernel;
   // default tail only
-  const bool solve_lean = !dbg_env && solve_env && solve_env[0] == 'l' && polish_flag == 2;
+  // ASVD_B200_LEAN_AUTO=1 (for the measurement that decides the default): lean wherever the quad solve would be picked
+  // and the batch has more block pairs than SMs, i.e. where two solve CTAs per SM save a wave.
+  const char* auto_env = getenv("ASVD_B200_LEAN_AUTO");
+  int sms_dev = 0;
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms_dev, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms_dev <= 0)
+      sms_dev = 148;
+  }
+  const bool lean_auto = auto_env && auto_env[0] == '1' && !solve_env && quad_pays && p.batch * p.pairs > sms_dev;
+  const bool solve_lean = !dbg_env && polish_flag == 2 && ((solve_env && solve_env[0] == 'l') || lean_auto);
   const bool solve_quad = !dbg_env && !solve_lean && (solve_env ? solve_env[0] == 'q' : quad_pays);
   const char* simt_env = getenv("ASVD_B200_SIMT");
   const bool use_tc = !(simt_env && simt_env[0] == '1');

@@ -78,7 +78,8 @@ int asvd_scaling_vector(const void* sdm, const void* fisher, int stat_dtype, int
  * Environment switches for A/B runs (read at every call): ASVD_B200_SOLVE=quad|oddeven, ASVD_B200_POLISH=NS,
  * ASVD_B200_GRAMPRE=0, ASVD_B200_RECOVER=simt, ASVD_B200_PRESORT=0, ASVD_B200_SIMT=1, ASVD_B200_TRACE=1,
  * ASVD_B200_OVERLAP=1 (two half-batches on two internal streams; same results bitwise, measured not faster),
- * ASVD_B200_SOLVE=lean (experimental split of the inner sweep: G-only kernel at two CTAs per SM + R replay kernel).
+ * ASVD_B200_SOLVE=lean (experimental split of the inner sweep: G-only kernel at two CTAs per SM + R replay kernel;
+ * ASVD_B200_LEAN_AUTO=1 selects it only where a batch has more block pairs than the device has SMs).
  * Blocks the calling thread until the factorisation is complete on `stream` (it polls a convergence flag
  * once per sweep). */
 size_t asvd_svd_workspace_bytes(int m, int n, int batch);

@@ -11,5 +11,7 @@ AB_REPS=3 timeout 120 python scripts/ab_lean.py quad:4 quad:8 quad:9 lean:8 lean
 # (default = odd-even outer solve on 2.7:1 shapes, quad inside the pre-conditioner; lean forces the lean solve in both)
 timeout 120 python scripts/ab_overlap.py 11008x4096x4 11008x4096x8 4096x11008x4 4096x11008x8 2>&1 | tee gpurun_out/r02_rect_default.jsonl
 ASVD_B200_SOLVE=lean timeout 120 python scripts/ab_overlap.py 11008x4096x4 11008x4096x8 4096x11008x4 4096x11008x8 2>&1 | tee gpurun_out/r02_rect_lean.jsonl
-# 4. the bench as the driver runs it
+# 4. the bench with the candidate defaults (lean where the batch has more pairs than SMs, nine weights per step)
+ASVD_B200_LEAN_AUTO=1 timeout 200 python bench.py --batch 9 --no-cpu-baseline > gpurun_out/r02_bench_1gpu_lean9.json 2> gpurun_out/r02_bench_1gpu_lean9.err; tail -c 300 gpurun_out/r02_bench_1gpu_lean9.json
+# 5. the bench as the driver runs it
 timeout 200 python bench.py > gpurun_out/r02_bench_1gpu.json 2> gpurun_out/r02_bench_1gpu.err; tail -c 500 gpurun_out/r02_bench_1gpu.json
