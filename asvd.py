@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from asvd4llm_b200.act_aware_utils import calib_fisher_info, calib_input_distribution
-from asvd4llm_b200.binary_search import binary_search_truncation_rank, search_allocation
+from asvd4llm_b200.binary_search import binary_search_truncation_rank, search_allocation, LinearIndex
 from asvd4llm_b200.evaluate_utils import evaluate_perplexity
 from asvd4llm_b200.sensitivity import calib_sensitivity_ppl, calib_sensitivity_stable_rank
 from asvd4llm_b200 import sharding
@@ -83,8 +83,9 @@ def main(args):
             if world == 1:
                 binary_search_truncation_rank(model, sensitivity, calib_loader, args)
             else:
-                chosen, default = search_allocation(model, sensitivity, calib_loader, args)
-                sharding.decompose_sharded(model, chosen, default, args)
+                index = LinearIndex(model)
+                chosen, default = search_allocation(model, sensitivity, calib_loader, args, index=index)
+                sharding.decompose_sharded(model, chosen, default, args, index=index)
         elif world == 1:
             sensitivity = calib_sensitivity_ppl(model, calib_loader, args, args.use_cache)
             binary_search_truncation_rank(model, sensitivity, calib_loader, args)
@@ -92,8 +93,12 @@ def main(args):
             owners = sharding.owner_map(model, world)
             shard = calib_sensitivity_ppl(model, calib_loader, args, args.use_cache, layer_filter=lambda n: owners[n] == rank)
             sensitivity = sharding.gather_sensitivity(model, shard)
-            chosen, default = search_allocation(model, sensitivity, calib_loader, args)
-            sharding.decompose_sharded(model, chosen, default, args)
+            index = LinearIndex(model)
+            chosen, default = search_allocation(model, sensitivity, calib_loader, args, index=index)
+            stats = sharding.decompose_sharded(model, chosen, default, args, index=index)
+            if rank == 0:
+                print(f"sharded final pass: decompose {stats['decompose_s']:.2f} s, factor exchange {stats['exchange_s']:.2f} s "
+                      f"({stats['bytes'] / 1e9:.2f} GB received in {stats['collectives']} collectives)")
         if args.weight_quant != "none":
             print("weight quantization is out of scope of the B200 path; skipped")
     if rank == 0:

@@ -67,7 +67,7 @@ def load() -> C.CDLL:
         lib.asvd_svd_extract.restype = i32
         lib.asvd_svd_extract.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, vp, i64, vp, i64, vp]
         lib.asvd_lowrank_forward_scratch_bytes.restype = sz
-        lib.asvd_lowrank_forward_scratch_bytes.argtypes = [i64, i32]
+        lib.asvd_lowrank_forward_scratch_bytes.argtypes = [i64, i32, i32]
         lib.asvd_lowrank_forward.restype = i32
         lib.asvd_lowrank_forward.argtypes = [vp, i64, i64, i32, vp, i64, i32, vp, i64, i32, vp, vp, i64, i32, vp, sz, vp]
         lib.asvd_absstat_scratch_bytes.restype = sz
@@ -204,27 +204,86 @@ def scaled_svd(weights: Sequence[torch.Tensor], scales: Optional[Sequence[Option
     return Factorisation(m, n, batch, workspace, list(sweeps), status)
 
 
-def lowrank_forward(x: torch.Tensor, A: torch.Tensor, B: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
-    """y = (x B^T) A^T + bias — svd_linear.py:105-109."""
-    _require_cuda(x, A, B, bias)
+def pad_rank_stride(A: torch.Tensor) -> torch.Tensor:
+    """[m, r] view of A whose row pitch is r rounded up to 64 elements (whole 128-byte lines for 16-bit types) -- what
+    the tensor-core forward reads without a per-call copy.  Returns A itself when its rows are already 16-byte aligned."""
+    m, r = A.shape
+    if A.dtype == torch.float32 or (A.stride(1) == 1 and A.stride(0) % 8 == 0 and A.data_ptr() % 16 == 0):
+        return A
+    buf = torch.zeros(m, (r + 63) // 64 * 64, dtype=A.dtype, device=A.device)
+    buf[:, :r].copy_(A)
+    return buf[:, :r]
+
+
+def _lowrank_forward_raw(x2: torch.Tensor, A: torch.Tensor, B: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
     lib = load()
     r, n = B.shape
     m = A.shape[0]
+    M = x2.shape[0]
+    y = torch.empty(M, m, dtype=x2.dtype, device=x2.device)
+    if M == 0:
+        return y
+    nbytes = lib.asvd_lowrank_forward_scratch_bytes(M, r, m)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=x2.device)        # caching allocator: 512-byte aligned
+    with torch.cuda.device(x2.device):
+        _check(lib.asvd_lowrank_forward(x2.data_ptr(), x2.stride(0), M, n, B.data_ptr(), B.stride(0), r, A.data_ptr(),
+                                        A.stride(0), m, None if bias is None else bias.data_ptr(), y.data_ptr(), m,
+                                        dtype_code(x2.dtype), scratch.data_ptr(), nbytes, _stream()))
+    return y
+
+
+class _LowRankForward(torch.autograd.Function):
+    """Autograd wrapper: the forward is the C-ABI call; the backward (upstream's module is differentiable, but nothing
+    on the hot path differentiates through a decomposed layer -- calib_fisher_info runs on the raw model) is three
+    library matmuls."""
+
+    @staticmethod
+    def forward(ctx, x2, A, B, bias, A_kernel):
+        ctx.save_for_backward(x2, A, B)
+        ctx.has_bias = bias is not None
+        return _lowrank_forward_raw(x2, A_kernel, B, bias)
+
+    @staticmethod
+    def backward(ctx, g):
+        x2, A, B = ctx.saved_tensors
+        g = g.contiguous()
+        gt = g @ A                                             # [M, r]
+        gx = gt @ B if ctx.needs_input_grad[0] else None
+        gA = g.t() @ (x2 @ B.t()) if ctx.needs_input_grad[1] else None
+        gB = gt.t() @ x2 if ctx.needs_input_grad[2] else None
+        gb = g.sum(0) if (ctx.has_bias and ctx.needs_input_grad[3]) else None
+        return gx, gA, gB, gb, None
+
+
+def lowrank_forward(x: torch.Tensor, A: torch.Tensor, B: torch.Tensor, bias: Optional[torch.Tensor],
+                    A_kernel: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = (x B^T) A^T + bias — svd_linear.py:105-109.  A_kernel: optional pad_rank_stride(A) kept by the caller."""
+    _require_cuda(x, A, B, bias)
+    r, n = B.shape
+    m = A.shape[0]
+    if A.shape[1] != r or x.shape[-1] != n or (bias is not None and bias.numel() != m):
+        raise RuntimeError(f"shape mismatch: x {tuple(x.shape)}, BLinear.weight {tuple(B.shape)}, ALinear.weight {tuple(A.shape)}")
+    for name, t in (("BLinear.weight", B), ("ALinear.weight", A), ("ALinear.bias", bias)):
+        if t is None:
+            continue
+        if t.dtype != x.dtype:      # what F.linear raises for upstream's nn.Linear children
+            raise RuntimeError(f"expected input and {name} to have the same dtype, but got: {x.dtype} != {t.dtype}")
+        if t.device != x.device:
+            raise RuntimeError(f"expected all tensors to be on the same device, but found {x.device} and {t.device} ({name})")
+    dtype_code(x.dtype)
     x2 = x.reshape(-1, n)
     if not x2.is_contiguous():
         x2 = x2.contiguous()
-    A = A if A.is_contiguous() else A.contiguous()
+    A = A if A.stride(1) == 1 else A.contiguous()
     B = B if B.is_contiguous() else B.contiguous()
-    M = x2.shape[0]
-    y = torch.empty(M, m, dtype=x.dtype, device=x.device)
-    if M == 0:
-        return y.reshape(*x.shape[:-1], m)
-    nbytes = lib.asvd_lowrank_forward_scratch_bytes(M, r)
-    scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-    with torch.cuda.device(x.device):
-        _check(lib.asvd_lowrank_forward(x2.data_ptr(), x2.stride(0), M, n, B.data_ptr(), B.stride(0), r, A.data_ptr(),
-                                        A.stride(0), m, None if bias is None else bias.data_ptr(), y.data_ptr(), m,
-                                        dtype_code(x.dtype), scratch.data_ptr(), nbytes, _stream()))
+    if bias is not None and not bias.is_contiguous():
+        bias = bias.contiguous()
+    Ak = A if A_kernel is None else A_kernel
+    needs_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x, A, B, bias))
+    if needs_grad:
+        y = _LowRankForward.apply(x2, A, B, bias, Ak.detach())
+    else:
+        y = _lowrank_forward_raw(x2, Ak, B, bias)
     return y.reshape(*x.shape[:-1], m)
 
 

@@ -21,10 +21,63 @@ def _ratios_after_cut(sorted_list, cut, layer_names, default_ratio):
     return chosen
 
 
-def search_allocation(model, sensitivity_dict, calib_loader, args):
+class LinearIndex:
+    """name -> raw nn.Linear and raw -> (father, child name), captured ONCE before anything is replaced -- upstream's
+    module_dict / linear_info (binary_search.py:11-27).  The ppl-target search installs SVDLinears in every iteration;
+    every later step must still find the raw layers."""
+
+    def __init__(self, model):
+        self.by_name = dict(model.named_modules())
+        self.where = {lin: (father, name) for father, name, _, lin in enumerate_linears(model)}
+        # a weight tied to another module (OPT: lm_head <-> embed_tokens) must stay where it is: upstream's
+        # unconditional `raw_linear.to("cpu")` (:127) would drag the embedding to the CPU with it on a GPU run
+        self.uses = defaultdict(int)
+        for mod in model.modules():
+            for prm in mod._parameters.values():
+                if prm is not None:
+                    self.uses[id(prm)] += 1
+
+
+def _install(index, chosen, default_ratio, args, layer_filter=None, batch_limit_bytes=16 << 30, final=True,
+             decompose_default=False):
+    """Replaces every selected layer by its SVDLinear, same-shape layers batched per kernel call.
+    final=True is upstream's last pass (:112-128): default-ratio layers get the RAW linear back and replaced weights
+    move to the CPU.  decompose_default=True is the ppl-target loop (:64-76), which decomposes every layer at its ratio."""
+    groups = defaultdict(list)
+    done = 0
+    for layer, ratio in chosen.items():
+        raw = index.by_name[layer]
+        if layer_filter is not None and not layer_filter(layer):
+            if final:                                           # another rank's layer: hold the raw layer until its factors arrive
+                father, name = index.where[raw]
+                setattr(father, name, raw)
+            continue
+        if ratio == default_ratio and not decompose_default:
+            father, name = index.where[raw]
+            setattr(father, name, raw)                          # :116-117 (undoes a ppl-target search's replacement)
+            continue
+        groups[(tuple(raw.weight.shape), raw.weight.dtype, raw.weight.device)].append((layer, ratio, raw))
+    for (shape, _, _), items in groups.items():
+        m, n = shape
+        step = _lib.suggest_batch(m, n, limit_bytes=batch_limit_bytes)
+        for i in range(0, len(items), step):
+            part = items[i:i + step]
+            mods = from_linear_batch([raw for _, _, raw in part], [ratio for _, ratio, _ in part], alpha=args.alpha,
+                                     act_aware=args.act_aware, sigma_fuse=args.sigma_fuse, rank_align=args.rank_align)
+            for (layer, _, raw), mod in zip(part, mods):
+                if final and mod is not raw and index.uses[id(raw.weight)] <= 1:   # (ASVD_B200_KEEP_RAW_ON_FAILURE re-installs `raw`)
+                    raw.to("cpu")                               # upstream frees the replaced weight (:127)
+                father, name = index.where[raw]
+                setattr(father, name, mod)
+                done += 1
+    clear_cache()
+    return done
+
+
+def search_allocation(model, sensitivity_dict, calib_loader, args, index=None):
     """The search part (binary_search.py:29-110).  Returns ({layer: ratio}, default_ratio)."""
-    by_name = dict(model.named_modules())
-    where = {lin: (father, name) for father, name, _, lin in enumerate_linears(model)}
+    index = index or LinearIndex(model)
+    by_name = index.by_name
     if args.compress_kv_cache:
         ratio_target = args.kv_cache_ratio_target
         sensitivity_dict = {k: v for k, v in sensitivity_dict.items() if "k_proj" in k or "v_proj" in k}
@@ -51,14 +104,13 @@ def search_allocation(model, sensitivity_dict, calib_loader, args):
         tot = comp = 0
         if args.ppl_target > 0:
             assert not args.compress_kv_cache, "ppl_target is not supported when compressing kv_cache now"
+            # every layer of the table is decomposed at its current ratio -- including ratio 1, which upstream's
+            # from_linear turns into rank m*n // (m+n) (:64-76) -- always from the RAW layer
+            _install(index, chosen, default_ratio, args, final=False, decompose_default=True)
             for layer, ratio in chosen.items():
-                raw = by_name[layer]
-                father, name = where[raw]
-                setattr(father, name, SVDLinear.from_linear(raw, param_ratio=ratio, alpha=args.alpha,
-                                                            act_aware=args.act_aware, sigma_fuse=args.sigma_fuse,
-                                                            rank_align=args.rank_align))
-                tot += raw.weight.numel()
-                comp += raw.weight.numel() * ratio
+                numel = by_name[layer].weight.numel()
+                tot += numel
+                comp += numel * ratio
             ppl = evaluate_perplexity(model, input_ids, args.n_calib_samples)
             print(f"low={low} mid={mid}, high={high}, ppl={ppl}, param_ratio={comp / tot}")
             if ppl < args.ppl_target:
@@ -82,47 +134,17 @@ def search_allocation(model, sensitivity_dict, calib_loader, args):
     return _ratios_after_cut(flat, mid, sensitivity_dict.keys(), default_ratio), default_ratio   # stale mid (:106)
 
 
-def decompose_layers(model, chosen, default_ratio, args, layer_filter=None, batch_limit_bytes=16 << 30):
+def decompose_layers(model, chosen, default_ratio, args, layer_filter=None, batch_limit_bytes=16 << 30, index=None):
     """The final pass (binary_search.py:112-128), batching same-shape layers per kernel call.
-    Returns the number of layers replaced."""
-    by_name = dict(model.named_modules())
-    where = {lin: (father, name) for father, name, _, lin in enumerate_linears(model)}
-    # a weight tied to another module (OPT: lm_head <-> embed_tokens) must stay where it is: upstream's
-    # unconditional `raw_linear.to("cpu")` (:127) would drag the embedding to the CPU with it on a GPU run
-    uses = defaultdict(int)
-    for prm in model.parameters(recurse=True):
-        uses[id(prm)] += 0
-    for mod in model.modules():
-        for prm in mod._parameters.values():
-            if prm is not None:
-                uses[id(prm)] += 1
-    groups = defaultdict(list)
-    for layer, ratio in chosen.items():
-        if ratio == default_ratio or (layer_filter is not None and not layer_filter(layer)):
-            continue
-        raw = by_name[layer]
-        groups[(tuple(raw.weight.shape), raw.weight.dtype, raw.weight.device)].append((layer, ratio, raw))
-    done = 0
-    for (shape, _, _), items in groups.items():
-        m, n = shape
-        step = _lib.suggest_batch(m, n, limit_bytes=batch_limit_bytes)
-        for i in range(0, len(items), step):
-            part = items[i:i + step]
-            mods = from_linear_batch([raw for _, _, raw in part], [ratio for _, ratio, _ in part], alpha=args.alpha,
-                                     act_aware=args.act_aware, sigma_fuse=args.sigma_fuse, rank_align=args.rank_align)
-            for (layer, _, raw), mod in zip(part, mods):
-                if mod is not raw and uses[id(raw.weight)] <= 1:   # (ASVD_B200_KEEP_RAW_ON_FAILURE re-installs `raw` itself)
-                    raw.to("cpu")                               # upstream frees the replaced weight (:127)
-                father, name = where[raw]
-                setattr(father, name, mod)
-                done += 1
-    clear_cache()
-    return done
+    Returns the number of layers replaced.  `index` must be the LinearIndex captured before a ppl-target search."""
+    return _install(index or LinearIndex(model), chosen, default_ratio, args, layer_filter=layer_filter,
+                    batch_limit_bytes=batch_limit_bytes, final=True)
 
 
 def binary_search_truncation_rank(model, sensitivity_dict, calib_loader, args):
-    chosen, default_ratio = search_allocation(model, sensitivity_dict, calib_loader, args)
+    index = LinearIndex(model)
+    chosen, default_ratio = search_allocation(model, sensitivity_dict, calib_loader, args, index=index)
     st = time.time()
-    decompose_layers(model, chosen, default_ratio, args)
+    decompose_layers(model, chosen, default_ratio, args, index=index)
     ed = time.time()
     print(f"decompose time: {ed - st}")

@@ -9,6 +9,10 @@ namespace tc {
 template <typename T>
 int gemm_tn_tc(const T* A, int64_t lda, const T* B, int64_t ldb, T* C, int64_t ldc, const T* bias, int M, int N, int K,
                cudaStream_t st);
+// CTA-pair version (gemm_tc2.cu, tcgen05.mma.cta_group::2, 256-row tiles); bn_force = 0 lets it choose the tile width
+template <typename T>
+int gemm_tn_tc2(const T* A, int64_t lda, const T* B, int64_t ldb, T* C, int64_t ldc, const T* bias, int M, int N, int K,
+                cudaStream_t st, int bn_force);
 // fp32 C[M,N] = sum of bf16 plane products (see KSched in gemm_tc.cu): A = [a1|a2|a3] (a_planes x kseg columns),
 // B = [b1|b2]; optional per-column scale.  0 = launched, 1 = operands not eligible, < 0 = error
 int gemm_planes_f32(const __nv_bfloat16* A, int64_t lda, int a_planes, const __nv_bfloat16* B, int64_t ldb, int b_planes,

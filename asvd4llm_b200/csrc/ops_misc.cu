@@ -1,5 +1,6 @@
 // a1 (calibration statistic), a3 (scaling vector) and the first-round body of a7 (low-rank forward).
 #include <float.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.h"
@@ -127,13 +128,37 @@ static int absstat_run(const void* x, int64_t ldx, int64_t L, int n, int mode, v
   return ASVD_OK;
 }
 
+// rows of a 16-bit matrix copied to a leading dimension that TMA accepts (multiple of 8 elements = 16 bytes)
+template <typename T>
+__global__ void __launch_bounds__(256) pad_rows_kernel(const T* __restrict__ src, int64_t lds, int rows, int cols,
+                                                       T* __restrict__ dst, int64_t ldd) {
+  const int row = blockIdx.y;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ldd; c += gridDim.x * blockDim.x)
+    dst[(int64_t)row * ldd + c] = c < cols ? src[(int64_t)row * lds + c] : from_f32<T>(0.f);
+}
+
+static bool tma_ok(const void* p, int64_t ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld * 2) % 16 == 0; }
+
+// which tensor-core GEMM: the CTA-pair kernel (default) or the single-CTA multicast kernel (ASVD_B200_FWD=1cta, A/B runs)
+static bool fwd_use_pair() {
+  const char* e = getenv("ASVD_B200_FWD");
+  return !(e && e[0] == '1');
+}
+static int fwd_force_bn() {
+  const char* e = getenv("ASVD_B200_FWD_BN");
+  return e ? atoi(e) : 0;
+}
+
 template <typename T>
 static int forward_gemm(const T* A, int64_t lda, const T* B, int64_t ldb, T* C, int64_t ldc, const T* bias, int M, int N, int K,
                         cudaStream_t st) {
   prof_begin(K_FORWARD, st);
   int rc = 1;
-  if constexpr (!std::is_same<T, float>::value) rc = tc::gemm_tn_tc<T>(A, lda, B, ldb, C, ldc, bias, M, N, K, st);
-  if (rc == 1) {   // operands not TMA-eligible (unaligned rows): same contraction on the SIMT kernel
+  if constexpr (!std::is_same<T, float>::value) {
+    rc = fwd_use_pair() ? tc::gemm_tn_tc2<T>(A, lda, B, ldb, C, ldc, bias, M, N, K, st, fwd_force_bn())
+                        : tc::gemm_tn_tc<T>(A, lda, B, ldb, C, ldc, bias, M, N, K, st);
+  }
+  if (rc == 1) {   // fp32 modules, or caller tensors whose rows are not 16-byte aligned (in/out features not a multiple of 8)
     GemmBatch gb;
     memset(&gb, 0, sizeof(gb));
     cudaError_t e = launch_gemm128<T, T, T, false>(A, lda, B, ldb, C, ldc, M, N, K, nullptr, nullptr, bias, 1, gb, st);
@@ -144,15 +169,35 @@ static int forward_gemm(const T* A, int64_t lda, const T* B, int64_t ldb, T* C, 
   return ASVD_OK;
 }
 
+// pitch of the [M, r] intermediate and of a padded copy of A: whole 128-byte lines (64 16-bit elements), so that every
+// 128-byte TMA box row is one aligned line (a pitch of 1848 elements for r = 1843 splits each row over two)
+static int64_t fwd_pitch(int r) { return round_up(r, 64); }
+static size_t fwd_t_bytes(int64_t M, int r) { return (size_t)round_up((int64_t)M * fwd_pitch(r) * 4, 256); }
+
 template <typename T>
 static int forward_run(const void* x, int64_t ldx, int64_t M, int n, const void* B, int64_t ldb, int r, const void* A,
                        int64_t lda, int m, const void* bias, void* y, int64_t ldy, void* scratch, cudaStream_t st) {
+  // t[M, r] = x B^T, materialised in the module dtype as upstream's BLinear output is.  Its leading dimension is r rounded
+  // up to 64 elements so that any rank -- the rank formula produces 1843, 2686, 345 ... -- stays on the tensor-core path;
+  // an ALinear.weight whose own rows are not 16-byte aligned (contiguous [m, r], r % 8 != 0) is copied once into the
+  // scratch with the same padded pitch (callers that keep a padded copy, as SVDLinear does, skip this)
+  const int64_t ldt = fwd_pitch(r);
   T* t = reinterpret_cast<T*>(scratch);
-  // t[M, r] = x B^T  (materialised in the module dtype, as upstream's BLinear output is)
-  int rc = forward_gemm<T>((const T*)x, ldx, (const T*)B, ldb, t, r, (const T*)nullptr, (int)M, r, n, st);
+  const T* Ause = reinterpret_cast<const T*>(A);
+  int64_t lda_use = lda;
+  if constexpr (!std::is_same<T, float>::value) {
+    if (!tma_ok(A, lda) && tma_ok(x, ldx) && tma_ok(B, ldb) && tma_ok(y, ldy)) {
+      T* Apad = reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(scratch) + fwd_t_bytes(M, r));
+      ASVD_LAUNCH(K_FORWARD, st, (pad_rows_kernel<T><<<dim3((unsigned)((ldt + 255) / 256), m), 256, 0, st>>>(
+                                     reinterpret_cast<const T*>(A), lda, m, r, Apad, ldt)));
+      Ause = Apad;
+      lda_use = ldt;
+    }
+  }
+  int rc = forward_gemm<T>((const T*)x, ldx, (const T*)B, ldb, t, ldt, (const T*)nullptr, (int)M, r, n, st);
   if (rc) return rc;
   // y[M, m] = t A^T + bias
-  return forward_gemm<T>(t, r, (const T*)A, lda, (T*)y, ldy, (const T*)bias, (int)M, m, r, st);
+  return forward_gemm<T>(t, ldt, Ause, lda_use, (T*)y, ldy, (const T*)bias, (int)M, m, r, st);
 }
 
 extern "C" {
@@ -191,7 +236,10 @@ int asvd_absstat_accum(const void* x, int64_t ldx, int64_t L, int n, int dtype, 
   return ASVD_ERR_INVALID;
 }
 
-size_t asvd_lowrank_forward_scratch_bytes(int64_t M, int r) { return (M > 0 && r > 0) ? (size_t)M * r * 4 : 0; }
+size_t asvd_lowrank_forward_scratch_bytes(int64_t M, int r, int m) {
+  if (M <= 0 || r <= 0 || m <= 0) return 0;
+  return fwd_t_bytes(M, r) + (size_t)m * fwd_pitch(r) * 4;       // [M, pitch] intermediate + room for a padded copy of A
+}
 
 
 int asvd_lowrank_forward(const void* x, int64_t ldx, int64_t M, int n, const void* B, int64_t ldb, int r, const void* A,
@@ -200,7 +248,8 @@ int asvd_lowrank_forward(const void* x, int64_t ldx, int64_t M, int n, const voi
   ASVD_REQUIRE(x && B && A && y && scratch, "null pointer");
   ASVD_REQUIRE(M > 0 && M < (1ll << 31) && n > 0 && r > 0 && m > 0, "bad shape");
   ASVD_REQUIRE(ldx >= n && ldb >= n && lda >= r && ldy >= m, "bad leading dimension");
-  if (scratch_bytes < asvd_lowrank_forward_scratch_bytes(M, r)) { set_error("scratch too small"); return ASVD_ERR_WORKSPACE; }
+  if (scratch_bytes < asvd_lowrank_forward_scratch_bytes(M, r, m)) { set_error("scratch too small"); return ASVD_ERR_WORKSPACE; }
+  ASVD_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, "scratch must be 256-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (dtype) {
     case ASVD_F16: return forward_run<__half>(x, ldx, M, n, B, ldb, r, A, lda, m, bias, y, ldy, scratch, st);

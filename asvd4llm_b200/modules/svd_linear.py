@@ -74,7 +74,22 @@ class SVDLinear(nn.Module):
             y = inp.new_zeros(*inp.shape[:-1], self.ALinear.out_features)
             return y if self.ALinear.bias is None else y + self.ALinear.bias
         # y = (x B^T) A^T + b in one C-ABI call (asvd_lowrank_forward)
-        return _lib.lowrank_forward(inp, self.ALinear.weight, self.BLinear.weight, self.ALinear.bias)
+        return _lib.lowrank_forward(inp, self.ALinear.weight, self.BLinear.weight, self.ALinear.bias,
+                                    A_kernel=self._kernel_A())
+
+    def _kernel_A(self):
+        """ALinear.weight with a 16-byte-aligned row pitch.  The rank formula gives ranks like 1843 or 345; a contiguous
+        [m, r] 16-bit weight with r % 8 != 0 cannot be a TMA operand, so a padded copy is kept (rebuilt when the weight
+        tensor is replaced or modified in place through autograd-visible ops)."""
+        w = self.ALinear.weight
+        if not w.is_cuda or w.dtype == torch.float32 or (w.stride(0) % 8 == 0 and w.data_ptr() % 16 == 0):
+            return None
+        key = (w.data_ptr(), w._version, w.dtype, w.device, tuple(w.shape))
+        cache = self.__dict__.get("_a_pad")
+        if cache is None or cache[0] != key:
+            cache = (key, _lib.pad_rank_stride(w.detach()))
+            self.__dict__["_a_pad"] = cache                     # not a buffer: never part of the state dict
+        return cache[1]
 
 
 # ---------------------------------------------------------------------------------------------------------

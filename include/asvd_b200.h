@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define ASVD_B200_VERSION 100
+#define ASVD_B200_VERSION 200
 
 /* element types of caller tensors */
 enum { ASVD_F32 = 0, ASVD_F16 = 1, ASVD_BF16 = 2 };
@@ -102,9 +102,14 @@ int asvd_svd_extract(const void* workspace, int m, int n, int batch, int b, int 
 
 /* ---- a7: SVDLinear.forward — modules/svd_linear.py:105-109 and ASVDLinear.forward
  * (huggingface_repos/modeling_asvd_llama.py:11-12).  y = (x B^T) A^T + bias.
- *   x [M, n] ldx;  B [r, n] ldb;  A [m, r] lda;  bias [m] or NULL;  y [M, m] ldy;  all `dtype` (F16 / BF16)
- *   scratch: asvd_lowrank_forward_scratch_bytes(M, r) bytes for the [M, r] intermediate */
-size_t asvd_lowrank_forward_scratch_bytes(int64_t M, int r);
+ *   x [M, n] ldx;  B [r, n] ldb;  A [m, r] lda;  bias [m] or NULL;  y [M, m] ldy;  all `dtype`
+ *   scratch: asvd_lowrank_forward_scratch_bytes(M, r, m) bytes, 256-byte aligned: the [M, round_up(r, 64)] intermediate
+ *            (padded pitch: every rank runs on the tensor cores) plus room for a padded copy of A, made only when A's own
+ *            rows are not 16-byte aligned (contiguous [m, r] with r % 8 != 0; pass lda = round_up(r, 64), or any multiple of 8, to avoid it).
+ * F16 / BF16: tcgen05 GEMMs (CTA pairs, cta_group::2); F32 modules and x / B / y whose rows are not 16-byte aligned
+ * (in / out features not a multiple of 8) run on the fp32 SIMT kernel.  ASVD_B200_FWD=1cta selects the single-CTA
+ * multicast kernel (A/B runs). */
+size_t asvd_lowrank_forward_scratch_bytes(int64_t M, int r, int m);
 int asvd_lowrank_forward(const void* x, int64_t ldx, int64_t M, int n, const void* B, int64_t ldb, int r,
                          const void* A, int64_t lda, int m, const void* bias, void* y, int64_t ldy, int dtype,
                          void* scratch, size_t scratch_bytes, void* stream);

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared_symbols():
         assert hasattr(lib, name), name
-    assert lib.asvd_version() == 100
+    assert lib.asvd_version() == 200
 
 
 def test_rank_formula_host_entry_point():

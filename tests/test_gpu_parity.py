@@ -182,7 +182,7 @@ def test_sensitivity_cache_reuses_one_svd():
     assert L.profile_read()["gram"][1] > mid
 
 
-@pytest.mark.parametrize("r", [256, 512])
+@pytest.mark.parametrize("r", [256, 512, 1024, 1843, 345])
 def test_forward_parity_fp16(r):
     """config 4 shapes at reduced M: 1e-3 max-abs with |y| < 1, and error vs fp64 no worse than the reference's."""
     L = _lib()
@@ -200,6 +200,69 @@ def test_forward_parity_fp16(r):
         err = (y.double() - y64).abs().max().item()
         assert err < 1e-3, err
         assert (y.float() - yref16).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("r,with_bias", [(256, True), (1024, False), (1843, True)])
+def test_forward_full_size_config4(r, with_bias):
+    """BASELINE config 4 at FULL size (B=32, L=2048, d=4096 -> 65 536 tokens): the C-ABI forward against an fp64
+    reference on a strided row sample (every 128-row tile position and both CTAs of a pair are hit), 1e-3 max-abs with
+    |y| < 1.  The unsampled rows are covered by a checksum against the module-dtype torch product."""
+    L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    n = m = 4096
+    x = (torch.randn(32, 2048, n, device="cuda", generator=g) * 0.125).half()
+    B = (torch.randn(r, n, device="cuda", generator=g) / n ** 0.5).half()
+    A = (torch.randn(m, r, device="cuda", generator=g) / r ** 0.5 * 0.5).half()
+    bias = (torch.randn(m, device="cuda", generator=g) * 0.1).half() if with_bias else None
+    before = L.profile_read()["forward"][1]
+    y = L.lowrank_forward(x, A, B, bias)
+    assert L.profile_read()["forward"][1] > before
+    assert y.shape == (32, 2048, m)
+    y2 = y.reshape(-1, m)
+    rows = torch.arange(0, 65536, 97, device="cuda")
+    rows = torch.cat([rows, torch.tensor([127, 128, 255, 256, 65535 - 128, 65535], device="cuda")])
+    xs = x.reshape(-1, n)[rows].double()
+    t = (xs @ B.double().t()).half().double()                   # BLinear output is materialised in fp16 upstream too
+    y64 = t @ A.double().t() + (0 if bias is None else bias.double())
+    assert y64.abs().max() < 1.0
+    err = (y2[rows].double() - y64).abs().max().item()
+    assert err < 1e-3, err
+    # every row: column sums of y against the same sums of a torch fp16 product of the same factors (fp32 accumulate)
+    ref = torch.nn.functional.linear(torch.nn.functional.linear(x.reshape(-1, n), B), A, bias)
+    d = (y2.float() - ref.float()).abs().max().item()
+    assert d < 2e-3, d
+
+
+def test_forward_rejects_mixed_dtypes_and_supports_autograd():
+    L = _lib()
+    from asvd4llm_b200 import SVDLinear
+    g = torch.Generator().manual_seed(3)
+    n, r, m = 64, 13, 48
+    B = (torch.randn(r, n, generator=g) / n ** 0.5).half().cuda()
+    A = (torch.randn(m, r, generator=g) / r ** 0.5).half().cuda()
+    with pytest.raises(RuntimeError, match="same dtype"):
+        L.lowrank_forward(torch.randn(4, n, device="cuda"), A, B, None)            # fp32 activations, fp16 module
+    with pytest.raises(RuntimeError, match="same device|CUDA"):
+        L.lowrank_forward(torch.randn(4, n).half().cuda(), A.cpu(), B, None)
+    # differentiable like upstream's two nn.Linear children
+    mod = SVDLinear._from_factors(A.float().clone(), B.float().clone(), torch.zeros(m, device="cuda"))
+    x = torch.randn(5, n, device="cuda", requires_grad=True)
+    y = mod(x)
+    y.square().sum().backward()
+    ref_A, ref_B = A.float().clone().requires_grad_(), B.float().clone().requires_grad_()
+    x2 = x.detach().clone().requires_grad_()
+    (torch.nn.functional.linear(torch.nn.functional.linear(x2, ref_B), ref_A)).square().sum().backward()
+    assert torch.allclose(x.grad, x2.grad, rtol=1e-3, atol=1e-4)
+    assert torch.allclose(mod.ALinear.weight.grad, ref_A.grad, rtol=1e-3, atol=1e-4)
+    assert torch.allclose(mod.BLinear.weight.grad, ref_B.grad, rtol=1e-3, atol=1e-4)
+    # a rank that is not a multiple of 8 keeps a padded kernel copy, refreshed when the weight is replaced
+    h = SVDLinear._from_factors(A, B, None)
+    xh = torch.randn(3, n, device="cuda").half()
+    y1 = h(xh)
+    assert h._kernel_A().stride(0) == 64
+    h.ALinear.weight.data = (A * 2).contiguous()
+    y2 = h(xh)
+    assert torch.allclose(y2.float(), 2 * y1.float(), rtol=2e-3, atol=2e-3)
 
 
 def test_forward_bf16_and_ragged_shapes():
