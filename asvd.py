@@ -90,8 +90,9 @@ def main(args):
             sensitivity = calib_sensitivity_ppl(model, calib_loader, args, args.use_cache)
             binary_search_truncation_rank(model, sensitivity, calib_loader, args)
         else:
-            owners = sharding.owner_map(model, world)
-            shard = calib_sensitivity_ppl(model, calib_loader, args, args.use_cache, layer_filter=lambda n: owners[n] == rank)
+            # (layer, ratio) units dealt round-robin: the sweep is almost entirely model forwards (one SVD serves a
+            # layer's six ratios), so equal unit counts are equal work
+            shard = calib_sensitivity_ppl(model, calib_loader, args, args.use_cache, unit_filter=lambda u: u % world == rank)
             sensitivity = sharding.gather_sensitivity(model, shard)
             index = LinearIndex(model)
             chosen, default = search_allocation(model, sensitivity, calib_loader, args, index=index)
@@ -137,5 +138,7 @@ if __name__ == "__main__":
     parser.add_argument("--rank_align", type=int, default=1, help="align rank in SVD")
     parser.add_argument("--raw_model", action="store_true", help="use the raw model without ASVD")
     parser.add_argument("--use_bos", action="store_true", help="use bos token in calibration")
+    parser.add_argument("--eval_batch_size", type=int, default=8,
+                        help="(extension) calibration samples per forward in the sensitivity sweep's perplexity evaluations (upstream: 1)")
     parser.add_argument("--synthetic_model", type=str, default="", choices=[""] + list(SYNTHETIC), help="(extension) random-init architecture")
     main(parser.parse_args())

@@ -11,6 +11,14 @@ import torch.nn as nn
 from . import _lib
 
 
+def atomic_save(obj, path):
+    """torch.save through a temporary file + os.replace: under torchrun every rank computes the same table and writes the
+    same cache path; a reader (or another writer) never sees a half-written file."""
+    tmp = f"{path}.tmp{os.getpid()}"
+    torch.save(obj, tmp)
+    os.replace(tmp, path)
+
+
 def _cache_file(model, method):
     model_id = model.config._name_or_path
     return f"cache/{model_id.replace('/', '_')}_calib_input_distribution_{method}.pt"
@@ -53,7 +61,7 @@ def calib_input_distribution(model, calib_loader, method, use_cache=True):
         if isinstance(module, nn.Linear):
             module._forward_hooks.clear()                      # upstream clears every hook (:93)
             table[name] = module.scaling_diag_matrix
-    torch.save(table, cache_file)
+    atomic_save(table, cache_file)
 
 
 def calib_fisher_info(model, calib_loader, use_cache=True):
@@ -97,4 +105,4 @@ def calib_fisher_info(model, calib_loader, use_cache=True):
             module.fisher_info = module.fisher_info.div(len(calib_loader)).sqrt()     # :36
             module._forward_hooks.clear()                                             # :42
             table[name] = module.fisher_info
-    torch.save(table, cache_file)
+    atomic_save(table, cache_file)

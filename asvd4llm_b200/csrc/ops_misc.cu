@@ -144,6 +144,7 @@ static bool fwd_use_pair() {
   const char* e = getenv("ASVD_B200_FWD");
   return !(e && e[0] == '1');
 }
+// ASVD_B200_FWD unset or "pair": two CTA-pair GEMMs; "fused": one fused kernel for r <= 256; "1cta": single-CTA GEMMs
 static int fwd_force_bn() {
   const char* e = getenv("ASVD_B200_FWD_BN");
   return e ? atoi(e) : 0;
@@ -192,6 +193,20 @@ static int forward_run(const void* x, int64_t ldx, int64_t M, int n, const void*
                                      reinterpret_cast<const T*>(A), lda, m, r, Apad, ldt)));
       Ause = Apad;
       lda_use = ldt;
+    }
+  }
+  if constexpr (!std::is_same<T, float>::value) {
+    // ASVD_B200_FWD=fused: ranks up to 256 in ONE kernel, the intermediate stays in shared memory (gemm_fused.cu).
+    // Correct and tested, but measured slower than the two CTA-pair GEMMs (280 vs 251 us at r = 256, 65 536 tokens:
+    // profiles/r02_fwd_ab.jsonl), so it is not the default.
+    const char* fwd_env = getenv("ASVD_B200_FWD");
+    if (r <= 256 && fwd_env && fwd_env[0] == 'f') {
+      prof_begin(K_FORWARD, st);
+      const int frc = tc::lowrank_fused<T>((const T*)x, ldx, (int)M, n, (const T*)B, ldb, r, Ause, lda_use, m, (const T*)bias,
+                                           (T*)y, ldy, st);
+      prof_end(K_FORWARD, st);
+      if (frc == 0) return ASVD_OK;
+      if (frc < 0) { set_error("fused forward launch failed (%d): %s", frc, cudaGetErrorString(cudaGetLastError())); return ASVD_ERR_CUDA; }
     }
   }
   int rc = forward_gemm<T>((const T*)x, ldx, (const T*)B, ldb, t, ldt, (const T*)nullptr, (int)M, r, n, st);

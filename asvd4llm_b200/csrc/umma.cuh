@@ -175,8 +175,26 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t cta_ra
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
   return r;
 }
+// wait that also acquires writes released at cluster scope by the arriving threads (a peer CTA's shared-memory stores)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+// Arrival on a barrier of a (possibly remote) CTA of the cluster.  Default semantics (release at CTA scope), as the
+// vendored CUTLASS ClusterBarrier::arrive(cta_id) does: an explicit `.release.cluster` compiles to MEMBAR.ALL.GPU +
+// ERRBAR in front of every arrival (profiles/r02_ncu_fwd_pair256: 34 % of the epilogue warps' samples).  What the waiter
+// needs ordered is covered elsewhere: tensor-memory reads by tcgen05.wait::ld + tcgen05.fence::before_thread_sync,
+// generic-proxy stores to shared memory by fence.proxy.async in the storing thread.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // tile load into THIS CTA's shared memory, bytes counted on the barrier at cluster address `bar_cluster_addr`
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* desc, uint32_t bar_cluster_addr, int x, int y) {

@@ -137,27 +137,53 @@ def _fallback(linear: nn.Linear):
 
 
 def factorise(linears: Sequence[nn.Linear], act_aware: bool, alpha: float, tol: float = 0.0, max_sweeps: int = 0):
-    """One batched asvd_scaled_svd call over same-shape linears.  Returns (_lib.Factorisation | None, dev)."""
+    """Batched asvd_scaled_svd over same-shape linears.  Returns ([(Factorisation, index in it) | None per layer], dev).
+
+    Upstream's failure path is per layer (svd_linear.py:66-68, 80-98), so a non-finite weight must not take the healthy
+    layers of its batch with it: weights / scales with NaN or Inf are screened out before the launch (one reduction per
+    weight instead of 30 wasted sweeps), and should the kernel still report non-finite values (overflow inside), the
+    batch is re-run layer by layer."""
     w0 = linears[0].weight.data
     dev = _compute_device(w0)
-    weights, scales = [], []
+    weights, scales, healthy = [], [], []
     for lin in linears:
-        w = lin.weight.data
-        weights.append(w.to(dev, non_blocking=True))
+        w = lin.weight.data.to(dev, non_blocking=True)
+        sc = None
         if act_aware:
             sdm, fisher = _stat(lin, "scaling_diag_matrix"), _stat(lin, "fisher_info")
             if sdm is None and fisher is None:
                 # upstream: `scaling_diag_matrix = 1; ... += 1e-6` then `.view` on a python float (:48-60)
                 raise AttributeError("'float' object has no attribute 'view'")
-            scales.append(_lib.scaling_vector(sdm, fisher, alpha, lin.in_features, dev))
-        else:
-            scales.append(None)
-    try:
-        return _lib.scaled_svd(weights, scales, tol=tol, max_sweeps=max_sweeps), dev
-    except _lib.AsvdError as e:
-        if e.status == _lib.ERR_NONFINITE:
-            return None, dev
-        raise
+            sc = _lib.scaling_vector(sdm, fisher, alpha, lin.in_features, dev)
+        weights.append(w)
+        scales.append(sc)
+        healthy.append(torch.isfinite(w).all() & (torch.isfinite(sc).all() if sc is not None else True))
+    healthy = [bool(h) for h in torch.stack([torch.as_tensor(h, device=dev) for h in healthy]).tolist()]
+    out = [None] * len(linears)
+    idx = [i for i, h in enumerate(healthy) if h]
+
+    def run(ids):
+        fact = _lib.scaled_svd([weights[i] for i in ids], [scales[i] for i in ids], tol=tol, max_sweeps=max_sweeps)
+        if fact.status == _lib.ERR_NOT_CONVERGED:
+            print(f"warning: asvd_scaled_svd hit its sweep limit above tolerance on a batch of {len(ids)} "
+                  f"[{w0.shape[0]}x{w0.shape[1]}] weights (sweeps {fact.sweeps}); factors are installed as they are")
+        for k, i in enumerate(ids):
+            out[i] = (fact, k)
+
+    if idx:
+        try:
+            run(idx)
+        except _lib.AsvdError as e:
+            if e.status != _lib.ERR_NONFINITE:
+                raise
+            if len(idx) > 1:
+                for i in idx:
+                    try:
+                        run([i])
+                    except _lib.AsvdError as e1:
+                        if e1.status != _lib.ERR_NONFINITE:
+                            raise
+    return out, dev
 
 
 def from_linear_batch(linears: Sequence[nn.Linear], param_ratios: Sequence[float], act_aware=False, ic_split=1,
@@ -176,22 +202,23 @@ def from_linear_batch(linears: Sequence[nn.Linear], param_ratios: Sequence[float
             w = lin.weight.data
             out.append(SVDLinear._from_factors(w.new_empty(m, 0), w.new_empty(0, n), lin.bias.data if lin.bias is not None else None))
         return out
-    fact = None
+    facts = None
     if len(linears) == 1:
         key = _key(linears[0], act_aware, alpha)
-        if _CACHE["key"] == key:
-            fact, dev = _CACHE["fact"], _CACHE["fact"].workspace.device if _CACHE["fact"] is not None else None
-    if fact is None:
-        fact, dev = factorise(linears, act_aware, alpha)
+        if _CACHE["key"] == key and _CACHE["fact"] is not None:
+            facts, dev = _CACHE["fact"], _CACHE["fact"][0][0].workspace.device
+    if facts is None:
+        facts, dev = factorise(linears, act_aware, alpha)
         if len(linears) == 1:
-            _CACHE.update(key=_key(linears[0], act_aware, alpha), fact=fact)
+            _CACHE.update(key=_key(linears[0], act_aware, alpha), fact=facts if facts[0] is not None else None)
     out = []
     pending_host = False
-    for b, (lin, r) in enumerate(zip(linears, ranks)):
-        if fact is None:
-            print("nan in S")                                    # upstream message (:82)
+    for lin, r, fb in zip(linears, ranks, facts):
+        if fb is None:
+            print("nan in S")                                    # upstream message (:82); THIS layer only
             out.append(_fallback(lin))
             continue
+        fact, b = fb
         w = lin.weight.data
         if r == 0:
             out.append(SVDLinear._from_factors(w.new_empty(m, 0), w.new_empty(0, n), lin.bias.data if lin.bias is not None else None))

@@ -5,6 +5,7 @@ import os
 import torch
 import torch.nn as nn
 
+from .act_aware_utils import atomic_save
 from .evaluate_utils import evaluate_perplexity
 from .modules.svd_linear import SVDLinear, clear_cache
 
@@ -34,32 +35,45 @@ def sensitivity_cache_file(model, args):
 
 
 @torch.no_grad()
-def calib_sensitivity_ppl(model, calib_loader, args, use_cache=True, layer_filter=None):
-    """layer_filter (extension): callable(full_name) -> bool restricting the sweep to a shard of layers; the
-    multi-GPU driver merges the shards (asvd4llm_b200.sharding)."""
+def calib_sensitivity_ppl(model, calib_loader, args, use_cache=True, layer_filter=None, unit_filter=None):
+    """Extensions, both off by default:
+      * layer_filter: callable(full_name) -> bool, or unit_filter: callable(unit index) -> bool over the flattened
+        (layer, ratio) sweep order -- restrict the sweep to a shard; the multi-GPU driver merges the shards
+        (asvd4llm_b200.sharding.gather_sensitivity).  With one SVD serving the six ratios of a layer the sweep is > 95 %
+        model forwards, so (layer, ratio) units balance the ranks better than layers at the cost of one extra SVD per
+        rank that shares a layer;
+      * args.eval_batch_size (asvd.py --eval_batch_size): calibration samples per model forward in evaluate_perplexity
+        (upstream: 1).  Same per-sample losses up to floating-point reassociation inside the batched GEMMs."""
     cache_file = sensitivity_cache_file(model, args)
-    if os.path.exists(cache_file) and use_cache and layer_filter is None:
+    sharded = layer_filter is not None or unit_filter is not None
+    if os.path.exists(cache_file) and use_cache and not sharded:
         return torch.load(cache_file, map_location="cpu")
     model.eval()
     ratios = KV_RATIOS if args.compress_kv_cache else RATIOS
     input_ids = torch.cat([b["input_ids"] for b in calib_loader], 0)
     print(f"input_ids.shape={input_ids.shape}")
+    eval_bs = max(1, int(getattr(args, "eval_batch_size", 1) or 1))
     table = {}
+    unit = 0
     for father, name, full_name, raw in enumerate_linears(model):
         if layer_filter is not None and not layer_filter(full_name):
+            unit += len(ratios)
             continue
-        table[full_name] = {}
         for ratio in ratios:
+            mine = unit_filter is None or unit_filter(unit)
+            unit += 1
+            if not mine:
+                continue
             svd_linear = SVDLinear.from_linear(raw, param_ratio=ratio, alpha=args.alpha, act_aware=True,
                                                rank_align=args.rank_align)       # act_aware hard-coded (:50)
             setattr(father, name, svd_linear)
-            ppl = evaluate_perplexity(model, input_ids, args.n_calib_samples)
-            table[full_name][ratio] = ppl
+            ppl = evaluate_perplexity(model, input_ids, args.n_calib_samples, batch_size=eval_bs)
+            table.setdefault(full_name, {})[ratio] = ppl
             print(f"{full_name} {ratio} {ppl}")
         setattr(father, name, raw)
     clear_cache()
-    if layer_filter is None:
-        torch.save(table, cache_file)
+    if not sharded:
+        atomic_save(table, cache_file)
     return table
 
 
@@ -85,5 +99,5 @@ def calib_sensitivity_stable_rank(model, calib_loader, args, use_cache=True):
         sigma = _lib.scaled_svd([w.to(dev)], [None]).sigma(0)
         sr = ((sigma.double() ** 2).sum() / sigma[0].double() ** 2).sqrt().to(w.dtype).to(w.device)
         table[full_name] = {ratio: -sr * ratio ** 0.1 for ratio in ratios}
-    torch.save(table, cache_file)
+    atomic_save(table, cache_file)
     return table

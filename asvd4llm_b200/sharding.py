@@ -73,8 +73,11 @@ def gather_sensitivity(model: nn.Module, shard: Dict[str, Dict[float, float]]) -
         dist.all_gather_object(parts, shard)
     merged = {}
     for part in parts:
-        merged.update(part)
-    return {full: merged[full] for _, _, full, _ in enumerate_linears(model) if full in merged}
+        for layer, row in part.items():
+            merged.setdefault(layer, {}).update(row)
+    # rows sharded by (layer, ratio) unit arrive in pieces: restore the ratio order of the sweep (ascending), which is
+    # the insertion order upstream's table has and binary_search.py:41-49 iterates
+    return {full: dict(sorted(merged[full].items())) for _, _, full, _ in enumerate_linears(model) if full in merged}
 
 
 def _pack(tensors):

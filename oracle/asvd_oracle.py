@@ -359,3 +359,63 @@ def decompose_model(model, chosen: Dict[str, float], default_ratio, alpha, act_a
         father, name = info[raw]
         setattr(father, name, from_linear(raw, ratio, act_aware=act_aware, alpha=alpha, sigma_fuse=sigma_fuse,
                                           rank_align=rank_align, method=method))
+
+
+def binary_search_truncation_rank(model, sensitivity: Dict[str, Dict[float, float]], calib_loader, ppl_target: float = -1,
+                                  param_ratio_target: float = -1, alpha: float = 0.5, act_aware: bool = True,
+                                  sigma_fuse: str = "UV", rank_align: int = 1, n_calib_samples: int = 3,
+                                  method: str = "lowrank") -> List[str]:
+    """binary_search.py:10-131 in full (weight mode), including the --ppl_target branch (:64-87): every iteration
+    decomposes EVERY layer of the table from its raw nn.Linear at the current ratio (ratio 1 included: from_linear then
+    gives rank m*n // (m+n)), evaluates the calibration perplexity and bisects on it; the final pass (:104-128) re-uses
+    the LAST mid, restores raw layers at the default ratio and decomposes the others.  Returns upstream's log lines.
+    method='lowrank' consumes the global torch RNG exactly like upstream's torch.svd_lowrank calls."""
+    by_name = dict(model.named_modules())
+    info = {lin: (father, name) for father, name, _, lin in enumerate_linears(model)}      # captured before any replacement
+    default = 1
+    log = [f"=== compress weight target: ppl={ppl_target}, ratio_target={param_ratio_target} ==="]
+    flat = [(layer, ratio, ppl) for layer, table in sensitivity.items() for ratio, ppl in table.items() if ratio < 1]
+    flat = sorted(flat, key=lambda t: -t[2])
+    low, high, mid = 0, len(flat) - 1, None
+    ids = torch.cat([b["input_ids"] for b in calib_loader], 0)
+    while low < high:
+        mid = (low + high) // 2
+        chosen = {k: default for k in sensitivity}
+        for layer, ratio, _ in flat[mid:]:
+            chosen[layer] = min(chosen[layer], ratio)
+        tot = comp = 0
+        if ppl_target > 0:
+            for layer, ratio in chosen.items():
+                raw = by_name[layer]
+                father, name = info[raw]
+                setattr(father, name, from_linear(raw, ratio, act_aware=act_aware, alpha=alpha, sigma_fuse=sigma_fuse,
+                                                  rank_align=rank_align, method=method))
+                tot += raw.weight.numel()
+                comp += raw.weight.numel() * ratio
+            ppl = evaluate_perplexity(model, ids, n_calib_samples)
+            log.append(f"low={low} mid={mid}, high={high}, ppl={ppl}, param_ratio={comp / tot}")
+            if ppl < ppl_target:
+                high = mid
+            else:
+                low = mid + 1
+        else:
+            for layer, ratio in chosen.items():
+                tot += by_name[layer].weight.numel()
+                comp += by_name[layer].weight.numel() * ratio
+            now = comp / tot
+            log.append(f"low={low} mid={mid}, high={high}, now_ratio={now}, params=({comp}/{tot})")
+            if now > param_ratio_target:
+                high = mid
+            else:
+                low = mid + 1
+    log.append("=== Searching done, decomposing layers... ===")
+    chosen = {k: default for k in sensitivity}
+    for layer, ratio, _ in flat[mid:]:
+        chosen[layer] = min(chosen[layer], ratio)
+    for layer, ratio in chosen.items():
+        raw = by_name[layer]
+        father, name = info[raw]
+        setattr(father, name, raw if ratio == default else from_linear(raw, ratio, act_aware=act_aware, alpha=alpha,
+                                                                       sigma_fuse=sigma_fuse, rank_align=rank_align,
+                                                                       method=method))
+    return log

@@ -16,12 +16,19 @@ def check(M, n, r, m, bias=True, dtype=torch.float16):
     ref = t @ A.double().t() + (0 if b is None else b.double())
     err = (y.double() - ref).abs().max().item()
     print(json.dumps({"check": [M, n, r, m], "dtype": str(dtype), "bias": bias, "max_abs_err": err, "ymax": ref.abs().max().item(),
-                      "fwd": os.environ.get("ASVD_B200_FWD", "pair"), "bn": os.environ.get("ASVD_B200_FWD_BN")}), flush=True)
+                      "fwd": os.environ.get("ASVD_B200_FWD", "default"), "bn": os.environ.get("ASVD_B200_FWD_BN")}), flush=True)
     return err
 
 
 if "--no-check" not in sys.argv:
-    for bn in (None, "64", "128", "192", "256"):
+    os.environ["ASVD_B200_FWD"] = "fused"                 # fused kernel for r <= 256
+    for shp in [(128, 64, 64, 128), (1, 64, 8, 32), (256, 512, 128, 256), (300, 512, 100, 384), (1000, 1024, 200, 1000),
+                (2048, 4096, 256, 4096), (2048 * 3 + 77, 768, 153, 3072), (19000, 1024, 256, 1024), (40000, 512, 64, 520)]:
+        check(*shp)
+    check(512, 1024, 256, 1024, dtype=torch.bfloat16)
+    check(513, 1024, 77, 1024, bias=False, dtype=torch.bfloat16)
+    os.environ["ASVD_B200_FWD"] = "pair"
+    for bn in (None, "64", "192"):
         if bn is None: os.environ.pop("ASVD_B200_FWD_BN", None)
         else: os.environ["ASVD_B200_FWD_BN"] = bn
         for shp in [(128, 64, 64, 128), (1, 64, 8, 32), (256, 512, 128, 256), (300, 512, 100, 384), (1000, 1024, 345, 1000),
@@ -49,11 +56,11 @@ def timeit(fn, reps=10):
     return ts[len(ts) // 2] * 1e3, ts[0] * 1e3
 
 
-for r in (256, 512, 1024, 1843):
+for r in (128, 256, 512, 1024, 1843):
     B = (torch.randn(r, n, device=dev) / n ** 0.5).half(); A = (torch.randn(m, r, device=dev) / r ** 0.5).half()
     Ak = _lib.pad_rank_stride(A)
     fl = 2.0 * M * r * (n + m)
-    cfgs = [("pair", None), ("pair", "256"), ("pair", "192"), ("pair", "128"), ("1cta", None)]
+    cfgs = [("fused", None), ("pair", None), ("1cta", None)] if r <= 256 else [("pair", None), ("1cta", None)]
     for fwd, bn in cfgs:
         os.environ["ASVD_B200_FWD"] = fwd
         if bn is None: os.environ.pop("ASVD_B200_FWD_BN", None)
@@ -61,6 +68,6 @@ for r in (256, 512, 1024, 1843):
         if fwd == "1cta" and r % 8: continue
         med, best = timeit(lambda: _lib.lowrank_forward(x, A, B, None, A_kernel=Ak))
         print(json.dumps({"r": r, "impl": fwd, "bn": bn, "us_median": round(med, 1), "us_best": round(best, 1), "tflops_median": round(fl / med / 1e6, 1)}), flush=True)
-    os.environ["ASVD_B200_FWD"] = "pair"; os.environ.pop("ASVD_B200_FWD_BN", None)
+    os.environ.pop("ASVD_B200_FWD", None); os.environ.pop("ASVD_B200_FWD_BN", None)
     med, best = timeit(lambda: torch.nn.functional.linear(torch.nn.functional.linear(x, B), A))
     print(json.dumps({"r": r, "impl": "cublas_pair(torch F.linear x2)", "us_median": round(med, 1), "us_best": round(best, 1), "tflops_median": round(fl / med / 1e6, 1)}), flush=True)

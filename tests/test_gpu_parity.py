@@ -265,6 +265,25 @@ def test_forward_rejects_mixed_dtypes_and_supports_autograd():
     assert torch.allclose(y2.float(), 2 * y1.float(), rtol=2e-3, atol=2e-3)
 
 
+def test_forward_fused_kernel_matches_pair_kernels(monkeypatch):
+    """ASVD_B200_FWD=fused (one kernel, intermediate in shared memory, ranks <= 256) against the default two-GEMM path:
+    both round the intermediate to the module dtype, so the results agree to fp16 output rounding; ragged M / m / r and
+    the split tail tiles (M = 19 000: 75 tiles on 74 clusters) included."""
+    L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    for (M, n, r, m) in [(300, 512, 100, 384), (19000, 1024, 256, 1024), (2048, 4096, 256, 4096), (6221, 768, 153, 3072)]:
+        x = (torch.randn(M, n, device="cuda", generator=g) * 0.125).half()
+        B = (torch.randn(r, n, device="cuda", generator=g) / n ** 0.5).half()
+        A = (torch.randn(m, r, device="cuda", generator=g) / r ** 0.5 * 0.5).half()
+        bias = (torch.randn(m, device="cuda", generator=g) * 0.1).half()
+        monkeypatch.delenv("ASVD_B200_FWD", raising=False)
+        y0 = L.lowrank_forward(x, A, B, bias)
+        monkeypatch.setenv("ASVD_B200_FWD", "fused")
+        y1 = L.lowrank_forward(x, A, B, bias)
+        monkeypatch.delenv("ASVD_B200_FWD", raising=False)
+        assert (y0.float() - y1.float()).abs().max().item() < 1e-3, (M, n, r, m)
+
+
 def test_forward_bf16_and_ragged_shapes():
     L = _lib()
     g = torch.Generator().manual_seed(1)
@@ -642,3 +661,219 @@ def test_lean_solve_matches_quad_bitwise(m, n, batch, monkeypatch):
         A1, B1 = ref.extract(min(m, n) // 2, "UV", torch.float16, b)
         A2, B2 = got.extract(min(m, n) // 2, "UV", torch.float16, b)
         assert torch.equal(A1, A2) and torch.equal(B1, B2)
+
+
+# ------------------------------------------------------------------------------------------------ full-size shapes (§8d configs 3/5)
+FULL_SIZE_SHAPES = [(11008, 4096, 0.9), (4096, 11008, 0.9), (32000, 4096, 0.9), (13824, 5120, 0.95), (50272, 768, 0.9)]
+
+
+@pytest.mark.parametrize("m,n,ratio", FULL_SIZE_SHAPES)
+def test_full_size_rectangles_vs_fp64(m, n, ratio):
+    """Every rectangular shape of Llama-2-7B / 13B / OPT-125m at FULL size, through the default path (Gram
+    pre-conditioner where it applies), against an fp64 reference computed on the device:
+      * sigma: 1e-4 relative on every kept value (strict, no allowance) vs fp64 singular values;
+      * reconstruction: the scaled error of the fp32 factors sits on the Eckart-Young floor sqrt(sum_{j>r} sigma_j^2);
+      * the factor product is an orthogonal projection of W (size-independent property)."""
+    L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(1000 + m % 97)
+    W = (torch.randn(m, n, device="cuda", generator=g) * 0.02).half()
+    sdm = torch.exp(torch.randn(n, device="cuda", generator=g)).half()
+    scale = L.scaling_vector(sdm, None, 0.5, n, "cuda")
+    fact = L.scaled_svd([W], [scale])
+    assert fact.status == 0
+    r = min(L.rank_for_ratio(m, n, ratio, 1), min(m, n))
+    Xd = W.double() * scale.double()
+    ref = torch.linalg.svdvals(Xd)                               # fp64 on the device
+    sig = fact.sigma(0).double()
+    rel = ((sig[:r] - ref[:r]).abs() / ref[:r]).max().item()
+    assert rel < SIGMA_RTOL, f"{m}x{n}: kept-sigma rel err {rel}"
+    A, B = fact.extract(r, "UV", torch.float32, 0)
+    rec = ((A.double() @ B.double() - W.double()) * scale.double()).norm().item()
+    floor = (ref[r:] ** 2).sum().sqrt().item()
+    assert rec <= floor * (1 + 1e-4) + 1e-6 * ref[0].item(), (rec, floor)
+    assert rec / Xd.norm().item() < 1.0
+
+
+def test_ill_conditioned_sigma_strict_and_with_allowance():
+    """Outlier-heavy / power-law inputs (activation-scaled LLM weights are like this).  Reported separately:
+    (a) the STRICT 1e-4 relative error on kept sigma above 1e-3 sigma_max -- must hold;
+    (b) below that, fp32 arithmetic (ours and LAPACK's) resolves sigma to ~eps32 * sigma_max ABSOLUTE, so
+        the bound is 1e-4 * (sigma + 1e-2 sigma_max)/... as in check_factorisation; the measured strict relative error
+        there (up to ~9e-4 at kappa_kept 2e5, profiles/r01_illcond_check.jsonl) is a documented deviation."""
+    L = _lib()
+    for kind, seed in (("power", 5), ("gauss", 6)):
+        W, s = O.synthetic_weight(1024, 1024, seed=seed, kind=kind)
+        if kind == "gauss":
+            s[::17] *= 300.0                                       # outlier channels
+        scale = (s.half().float() ** 0.5 + 1e-6)
+        fact = L.scaled_svd([W.cuda()], [scale.cuda()])
+        ref = torch.linalg.svdvals(W.double() * scale.double())
+        sig = fact.sigma(0).cpu().double()
+        r = O.rank_for_ratio(1024, 1024, 0.9)
+        big = ref[:r] > 1e-3 * ref[0]
+        strict = ((sig[:r] - ref[:r]).abs() / ref[:r])[big].max().item()
+        assert strict < SIGMA_RTOL, (kind, strict)
+        allowance = ((sig[:r] - ref[:r]).abs() / (ref[:r] + 1e-2 * ref[0])).max().item()
+        assert allowance < SIGMA_RTOL, (kind, allowance)
+        absolute = (sig[:r] - ref[:r]).abs().max().item() / ref[0].item()
+        assert absolute < 5e-6, (kind, absolute)                   # ~40 eps32 of sigma_max
+
+
+# ------------------------------------------------------------------------------------------------ --ppl_target (binary_search.py:64-87)
+@pytest.fixture(scope="module")
+def golden_ppl_target():
+    from conftest import GOLDEN
+    return torch.load(os.path.join(GOLDEN, "ppl_target_and_opt125m_shapes.pt"), weights_only=False)
+
+
+def test_ppl_target_search_against_exact_oracle(golden_pipeline, golden_ppl_target):
+    """The ppl-target branch end to end on the GPU against the oracle's restatement run with the EXACT factorisation
+    (the restatement itself is pinned to upstream's log in tests/test_oracle_golden.py).  Same bisection decisions,
+    same final modules -- raw nn.Linear restored where the final allocation says default -- same perplexity."""
+    from asvd4llm_b200 import SVDLinear
+    from asvd4llm_b200.binary_search import binary_search_truncation_rank
+    from asvd4llm_b200.evaluate_utils import evaluate_perplexity
+    g = golden_ppl_target["ppl_target"]
+    loader = golden_pipeline["loader"]
+    ids = torch.cat([b["input_ids"] for b in loader], 0)
+    for target in (g["target"], 0.5 * (golden_pipeline["ppl_raw"] + g["target"])):
+        ref_model = build_tiny_opt(golden_pipeline)
+        model = build_tiny_opt(golden_pipeline).cuda()
+        for mdl in (ref_model, model):
+            for n_, m_ in mdl.named_modules():
+                if isinstance(m_, nn.Linear):
+                    m_.scaling_diag_matrix = golden_pipeline["sdm_abs_mean"][n_].clone().to(m_.weight.device)
+        want = O.binary_search_truncation_rank(ref_model, golden_pipeline["sensitivity"], loader, ppl_target=target, method="exact")
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            binary_search_truncation_rank(model, golden_pipeline["sensitivity"], loader, _args(ppl_target=target, param_ratio_target=-1))
+        got = [l for l in buf.getvalue().splitlines() if l.startswith("low=") or l.startswith("===")]
+        ambiguous = False
+        for lg, lw in zip(got, want):
+            if "ppl=" in lw and not lw.startswith("==="):
+                pw = float(lw.split("ppl=")[1].split(",")[0]); pg = float(lg.split("ppl=")[1].split(",")[0])
+                assert lg.split(", ppl=")[0] == lw.split(", ppl=")[0], (lg, lw)
+                assert pg == pytest.approx(pw, rel=2e-3), (lg, lw)
+                if abs(pw - target) < 4e-3 * target:               # a decision inside the fp tolerance: stop comparing the path
+                    ambiguous = True
+                    break
+        if ambiguous:
+            continue
+        assert len(got) == len(want)
+        kinds_ref = {n: (type(m).__name__.replace("Oracle", ""), getattr(m, "truncation_rank", None))
+                     for n, m in ref_model.named_modules() if n in g["kinds"]}
+        kinds = {n: (type(m).__name__, getattr(m, "truncation_rank", None)) for n, m in model.named_modules() if n in g["kinds"]}
+        assert kinds == kinds_ref
+        assert evaluate_perplexity(model, ids, 3) == pytest.approx(O.evaluate_perplexity(ref_model, ids, 3), rel=2e-3)
+
+
+def test_opt125m_shapes_against_upstream(golden_ppl_target):
+    """BASELINE config 1's real layer shapes (768x768, 3072x768, 768x3072) against what the UNMODIFIED upstream
+    from_linear produced for the same seeded inputs (tests/golden/make_golden_ppl_target.py): same rank, reconstruction
+    no worse than upstream's (Eckart-Young), leading singular values and module output in agreement."""
+    from asvd4llm_b200 import SVDLinear
+    from conftest import GOLDEN
+    src = open(os.path.join(GOLDEN, "make_golden_ppl_target.py")).read()
+    ns = {}
+    exec(src[src.index("def opt125m_case"):src.index("OPT125M_SHAPES")], {"torch": torch}, ns)
+    for c in golden_ppl_target["opt125m_shapes"]:
+        W, sdm, x = ns["opt125m_case"](c["idx"], c["m"], c["n"])
+        lin = nn.Linear(c["n"], c["m"], bias=False)
+        lin.weight.data = W.clone()
+        lin = lin.cuda()
+        lin.scaling_diag_matrix = sdm.cuda()
+        mod = SVDLinear.from_linear(lin, c["ratio"], act_aware=True, alpha=0.5, sigma_fuse="UV")
+        assert mod.truncation_rank == c["rank"]
+        A, B = mod.ALinear.weight.data.double().cpu(), mod.BLinear.weight.data.double().cpu()
+        s = O.scaling_vector(sdm, None, 0.5).double()
+        rec = (((A @ B) - W.double()) * s).norm() / (W.double() * s).norm()
+        assert rec <= c["recon_scaled"] * (1 + 2e-3), (c["m"], c["n"], float(rec), c["recon_scaled"])
+        lead = max(8, c["rank"] // 8)
+        an = A.norm(dim=0)[:lead]
+        assert torch.allclose(an, c["a_col_norms"][:lead].double(), rtol=2e-2), (c["m"], c["n"])
+        y = mod(x.cuda()).float().cpu()
+        yu = c["y"].float()
+        assert (y - yu).abs().max().item() < 0.05 * yu.abs().max().item() + 1e-3
+
+
+# ------------------------------------------------------------------------------------------------ N1 / multi-GPU host paths on the device
+def test_sensitivity_sweep_units_and_batched_evaluation(golden_pipeline, tmp_path, monkeypatch):
+    """the sweep sharded by (layer, ratio) units over two 'ranks' and merged equals the unsharded table,
+    and evaluating several calibration samples per forward (--eval_batch_size) reproduces upstream's batch-1 table."""
+    from asvd4llm_b200.sensitivity import calib_sensitivity_ppl
+    from asvd4llm_b200 import sharding
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("cache")
+    loader = golden_pipeline["loader"]
+    model = build_tiny_opt(golden_pipeline).cuda()
+    for n_, m_ in model.named_modules():
+        if isinstance(m_, nn.Linear):
+            m_.scaling_diag_matrix = golden_pipeline["sdm_abs_mean"][n_].clone().cuda()
+    with contextlib.redirect_stdout(io.StringIO()):
+        full = calib_sensitivity_ppl(model, loader, _args(), use_cache=False)
+        parts = [calib_sensitivity_ppl(model, loader, _args(), use_cache=False, unit_filter=lambda u, r=r: u % 2 == r) for r in (0, 1)]
+        batched = calib_sensitivity_ppl(model, loader, _args(eval_batch_size=3), use_cache=False)
+    assert sum(len(row) for p in parts for row in p.values()) == sum(len(row) for row in full.values())
+    merged = {}
+    for p in parts:
+        for layer, row in p.items():
+            merged.setdefault(layer, {}).update(row)
+    merged = {k: dict(sorted(merged[k].items())) for k in full}
+    assert merged == full                                            # same kernels, same inputs: bitwise
+    for layer in full:
+        for ratio in full[layer]:
+            assert batched[layer][ratio] == pytest.approx(full[layer][ratio], rel=1e-5), (layer, ratio)
+
+
+def _sharded_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        import bench
+        from asvd4llm_b200 import sharding
+        from asvd4llm_b200.modules.svd_linear import SVDLinear
+        from asvd4llm_b200.sensitivity import enumerate_linears
+        torch.cuda.set_device(0)
+        model = bench.build_llama_like(torch.device("cuda", 0), n_blocks=2, hidden=256, inter=640, vocab=1000)
+        chosen = {full: 0.9 for _, _, full, _ in enumerate_linears(model)}
+        chosen[list(chosen)[3]] = 1                               # one layer stays raw
+        ns = argparse.Namespace(alpha=0.5, act_aware=True, sigma_fuse="UV", rank_align=1)
+        stats = sharding.decompose_sharded(model, chosen, 1, ns)
+        digest = {}
+        for name, mod in model.named_modules():
+            if isinstance(mod, SVDLinear):
+                digest[name] = (mod.truncation_rank, mod.ALinear.weight.data.cpu().view(torch.int16).long().sum().item(),
+                                mod.BLinear.weight.data.cpu().view(torch.int16).long().sum().item())
+        q.put((rank, "ok", digest, stats["collectives"]))
+    except Exception:  # noqa
+        import traceback
+        q.put((rank, traceback.format_exc(), None, None))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_final_pass_is_bitwise_independent_of_world_size():
+    """config 3's path at a small size: sharding.decompose_sharded with two ranks (gloo, both on cuda:0 -- the GPU box
+    of the test tier has one device) installs, on every rank, bit-identical factors to the single-rank run."""
+    import socket
+    import torch.multiprocessing as mp
+    results = {}
+    for world in (1, 2):
+        s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        got = [q.get(timeout=600) for _ in procs]
+        for p in procs:
+            p.join(timeout=60)
+        for rank, msg, digest, ncoll in got:
+            assert msg == "ok", f"world {world} rank {rank}:\n{msg}"
+            results[(world, rank)] = digest
+            assert ncoll == (0 if world == 1 else 2)
+    assert len(results[(1, 0)]) == 14                               # 15 linears, one kept raw
+    assert results[(2, 0)] == results[(1, 0)] and results[(2, 1)] == results[(1, 0)]

@@ -55,6 +55,16 @@ def _worker(rank, world, port, q):
         shard = {k: v for k, v in full.items() if owners[k] == rank}
         merged = sharding.gather_sensitivity(model, shard)
         assert merged == full and list(merged.keys()) == list(full.keys())
+        # ... or of its own (layer, ratio) units, dealt round-robin over the flattened sweep order (rows arrive in pieces)
+        shard, unit = {}, 0
+        for layer, row in full.items():
+            for ratio, ppl in row.items():
+                if unit % world == rank:
+                    shard.setdefault(layer, {})[ratio] = ppl
+                unit += 1
+        merged = sharding.gather_sensitivity(model, shard)
+        assert merged == full and list(merged.keys()) == list(full.keys())
+        assert all(list(merged[k].keys()) == list(full[k].keys()) for k in full)
         # final pass: the owner installs an (oracle-made) SVDLinear, everybody else receives it
         for n_, m_ in model.named_modules():
             if isinstance(m_, nn.Linear):
