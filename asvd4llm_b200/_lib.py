@@ -153,22 +153,35 @@ class Factorisation:
 
 
 def suggest_batch(m: int, n: int, device=None, limit_bytes: int = 32 << 30) -> int:
-    """How many same-shape weights to factorise per call: the inner eigen-solve runs one CTA per block pair
-    (128 vectors), one wave of them is the cheapest, and the two streaming passes need one wave's worth of pairs to
-    occupy every SM.  So: as many matrices as fit pairs * batch <= SM count, bounded by workspace memory."""
+    """How many same-shape weights to factorise per call.  Every kernel of a Jacobi round works one block pair (128
+    vectors) per CTA, and the inner eigen-solve -- 127 dependent rotation steps, one CTA per SM -- takes the same time for
+    one CTA as for a full wave of them, so batches are sized in whole WAVES of block pairs on the device's SMs.  Measured
+    (profiles/r02_ab_batch.jsonl, ms per matrix at 1 / 2 / 4 waves): 4096^2 57.3 / 49.9 / 47.4, 11008x4096 68.9 / 59.0 /
+    56.5, 4096x11008 84.0 / 72.5 / 69.9 -- the second wave fills the SMs the first leaves idle (4 x 32 pairs = 128 of 148)
+    and every further wave amortises the per-sweep host synchronisation.  Default: four waves (ASVD_B200_WAVES
+    overrides), at most 32 weights, bounded by the workspace budget."""
     _require_cuda()
     sms = torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device()).multi_processor_count
     pairs = (min(m, n) + 127) // 128
     lib = load()
-    waves = 1
-    if os.environ.get("ASVD_B200_TWO_WAVES") == "1" and max(m, n) < 2 * min(m, n):
-        # experimental (measured on 4096^2 only: 8 weights per call are 8 % faster per matrix than 4, because two waves
-        # of block pairs keep every SM streaming): two waves for the square-ish shapes
-        waves = 2
+    try:
+        waves = max(1, int(os.environ.get("ASVD_B200_WAVES", "4")))
+    except ValueError:
+        waves = 4
     b = int(max(1, min(waves * sms // max(pairs, 1), 32)))
     while b > 1 and lib.asvd_svd_workspace_bytes(int(m), int(n), b) > limit_bytes:      # part of the workspace is per call
         b -= 1
     return b
+
+
+def balanced_batches(n_items: int, cap: int):
+    """Split n_items into ceil(n_items / cap) batches of nearly equal size (128 layers with cap 18 -> 8 x 16, not
+    7 x 18 + 2: the inner solve of a 2-weight batch costs as much as that of a full wave)."""
+    if n_items <= 0:
+        return []
+    nb = (n_items + cap - 1) // cap
+    base, extra = divmod(n_items, nb)
+    return [base + (1 if i < extra else 0) for i in range(nb)]
 
 
 def scaled_svd(weights: Sequence[torch.Tensor], scales: Optional[Sequence[Optional[torch.Tensor]]] = None,

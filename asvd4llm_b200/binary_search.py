@@ -2,6 +2,7 @@
 (layer, ratio, ppl) list and the final decomposition of every selected layer.  Quirks kept on purpose
 (SURVEY.md §9): ratio >= 1 entries dropped outside kv mode, kv mode halves the ratio, the final allocation
 uses the LAST `mid` of the loop, log lines are upstream's."""
+import os
 import time
 from collections import defaultdict
 
@@ -59,17 +60,29 @@ def _install(index, chosen, default_ratio, args, layer_filter=None, batch_limit_
         groups[(tuple(raw.weight.shape), raw.weight.dtype, raw.weight.device)].append((layer, ratio, raw))
     for (shape, _, _), items in groups.items():
         m, n = shape
-        step = _lib.suggest_batch(m, n, limit_bytes=batch_limit_bytes)
-        for i in range(0, len(items), step):
-            part = items[i:i + step]
+        cap = _lib.suggest_batch(m, n, limit_bytes=batch_limit_bytes)
+        i = 0
+        for size in _lib.balanced_batches(len(items), cap):
+            part = items[i:i + size]
+            i += size
             mods = from_linear_batch([raw for _, _, raw in part], [ratio for _, ratio, _ in part], alpha=args.alpha,
                                      act_aware=args.act_aware, sigma_fuse=args.sigma_fuse, rank_align=args.rank_align)
             for (layer, _, raw), mod in zip(part, mods):
-                if final and mod is not raw and index.uses[id(raw.weight)] <= 1:   # (ASVD_B200_KEEP_RAW_ON_FAILURE re-installs `raw`)
-                    raw.to("cpu")                               # upstream frees the replaced weight (:127)
                 father, name = index.where[raw]
                 setattr(father, name, mod)
                 done += 1
+                if final and mod is not raw:
+                    # Upstream moves the replaced layer to the CPU (:127) to free GPU memory; nothing reads it afterwards
+                    # (module_dict / linear_info die with the function).  Here the index simply forgets the layer: the raw
+                    # weight is released as soon as nothing else holds it (a weight tied to another module, OPT's
+                    # lm_head <-> embed_tokens, stays where it is -- upstream's `.to("cpu")` would drag the embedding
+                    # along on a GPU run), without 13 GB of pageable device-to-host copies for a 7B model.
+                    # ASVD_B200_RAW_TO_CPU=1 restores upstream's literal behaviour for untied weights.
+                    if os.environ.get("ASVD_B200_RAW_TO_CPU") == "1" and index.uses[id(raw.weight)] <= 1:
+                        raw.to("cpu")
+                    index.by_name.pop(layer, None)
+                    index.where.pop(raw, None)
+            del mods, part
     clear_cache()
     return done
 

@@ -187,7 +187,7 @@ def run_reference(args, rank, world):
 
 def _default_batch_static():
     """suggest_batch(4096, 4096) on a 148-SM part, without touching a GPU (the CPU arm prints the same config keys)."""
-    return 2 * 148 // 32
+    return 4 * 148 // 32
 
 
 def llama_cpu_estimate(O):
@@ -259,8 +259,8 @@ def svd_workload(ctx):
     from asvd4llm_b200.modules.svd_linear import from_linear_batch
     import torch.nn as nn
     args, dev, rank, world = ctx.args, ctx.dev, ctx.rank, ctx.world
-    # the batch the product's own final pass uses for this shape (binary_search._install -> suggest_batch): two waves of
-    # block pairs on the SMs (9 at 4096^2 on 148 SMs); --batch overrides for experiments
+    # the batch the product's own final pass uses for this shape (binary_search._install -> suggest_batch): four waves
+    # of block pairs on the SMs (18 at 4096^2 on 148 SMs); --batch overrides for experiments
     B = args.batch if args.batch > 0 else _lib.suggest_batch(M, N_IN, dev)
     r = _lib.rank_for_ratio(M, N_IN, RATIO, 1)
     g = torch.Generator(device=dev).manual_seed(233 + rank)
@@ -284,14 +284,15 @@ def svd_workload(ctx):
     # A freshly booted box has been seen to take one step 40-80 % longer than its neighbours about a second into the load
     # (sw_power_cap flagged, clocks back at maximum right after): keep warming up, untimed, until two consecutive steps
     # agree to 5 % (at most 8 extra steps), so that the event falls outside the timed region.
-    extra, prev = 0, None
-    while extra < 8:
+    # (at least 3 s of load -- the event comes about a second in -- at most 12 extra steps)
+    extra, prev, t_load = 0, None, time.perf_counter()
+    while extra < 12:
         t0 = time.perf_counter()
         device_step(extra)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         extra += 1
-        if prev is not None and abs(dt - prev) <= 0.05 * prev:
+        if prev is not None and abs(dt - prev) <= 0.05 * prev and time.perf_counter() - t_load >= 3.0:
             break
         prev = dt
     ctx.barrier()

@@ -449,13 +449,18 @@ def test_llama13b_block_counts_reduced():
         check_factorisation(W, (s ** 0.5 + 1e-6).float(), 0.95, "UV")
 
 
-def test_suggest_batch_fills_one_wave():
+def test_suggest_batch_fills_whole_waves(monkeypatch):
     L = _lib()
     sms = torch.cuda.get_device_properties(0).multi_processor_count
-    for (m, n) in [(4096, 4096), (11008, 4096), (768, 768), (5120, 5120)]:
-        b = L.suggest_batch(m, n)
-        pairs = (min(m, n) + 127) // 128
-        assert 1 <= b <= 32 and b * pairs <= max(sms, pairs)
+    for waves in (1, 2, 4):
+        monkeypatch.setenv("ASVD_B200_WAVES", str(waves))
+        for (m, n) in [(4096, 4096), (11008, 4096), (768, 768), (5120, 5120)]:
+            b = L.suggest_batch(m, n)
+            pairs = (min(m, n) + 127) // 128
+            assert 1 <= b <= 32 and b * pairs <= max(waves * sms, pairs)
+    monkeypatch.delenv("ASVD_B200_WAVES")
+    assert L.suggest_batch(4096, 4096) == min(32, 4 * sms // 32)            # the batch bench.py times
+    assert L.balanced_batches(128, 18) == [16] * 8 and L.balanced_batches(5, 18) == [5] and L.balanced_batches(19, 18) == [10, 9]
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
@@ -791,9 +796,13 @@ def test_opt125m_shapes_against_upstream(golden_ppl_target):
         lead = max(8, c["rank"] // 8)
         an = A.norm(dim=0)[:lead]
         assert torch.allclose(an, c["a_col_norms"][:lead].double(), rtol=2e-2), (c["m"], c["n"])
+        # module output: the two rank-r approximations span different tail subspaces (svd_lowrank vs exact), so the outputs
+        # agree to within the truncation error itself (both are that far from x W^T), not to rounding
         y = mod(x.cuda()).float().cpu()
         yu = c["y"].float()
-        assert (y - yu).abs().max().item() < 0.05 * yu.abs().max().item() + 1e-3
+        yfull = x.float() @ W.float().t()
+        assert (y - yu).norm().item() < 1.5 * c["recon_scaled"] * yfull.norm().item() + 1e-3
+        assert (y - yfull).norm().item() < 1.5 * (yu - yfull).norm().item() + 1e-3
 
 
 # ------------------------------------------------------------------------------------------------ N1 / multi-GPU host paths on the device
