@@ -111,7 +111,7 @@ struct SvdPlan {
   int nb, rounds, pairs, chunks, chunk_cols;
   // byte offsets into the workspace
   size_t off_ptrs, off_pairs, off_X, off_Xr, off_Y, off_G, off_R, off_flag, off_maxoff, off_done, off_sigma, off_perm,
-      off_status, off_scale, off_norm, off_track, off_As, off_Bs, off_Yp, off_Gm, off_inner, off_aux;
+      off_status, off_scale, off_norm, off_track, off_As, off_Bs, off_Yp, off_Gm, off_inner, off_aux, off_prec;
   int gram_pre;    // 1: rectangular enough for the Gram pre-conditioner (workspace holds the inner square problem)
   size_t bytes;
 };

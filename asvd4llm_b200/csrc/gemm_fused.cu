@@ -15,7 +15,7 @@
 //            from L2; accumulators alternate between TMEM columns [256, 512) and [0, 256); epilogue (+ bias -> 16-bit ->
 //            swizzled staging -> TMA store) overlaps the next chunk's MMAs
 // Shared memory: T 64 KB | ring of six 16 KB units (phase 1 uses two per step: x, Bw; phase 2 one: Aw) | 4 x 16 KB store
-// staging.  Work items are (tile, chunk range): the tiles of the last, partial wave of clusters are split between
+// staging (one buffer per epilogue team of four warps; 16 epilogue warps).  Work items are (tile, chunk range): the tiles of the last, partial wave of clusters are split between
 // several clusters, each repeating phase 1 and taking a share of the chunks (65 536 tokens = 256 tiles on 74 clusters:
 // 3 full waves + 34 tiles on 68 clusters at 3/4 of a wave instead of a 4th full wave).
 #include "common.cuh"
@@ -29,15 +29,15 @@ namespace tc {
 namespace fz {
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int THREADS = 384;
+constexpr int THREADS = 640;            // warps 0-3: producer / MMA / TMEM alloc / spare; warps 4-19: drain + epilogue
 constexpr int UNIT = 16384;             // [128 rows x 128 B]
 constexpr int NU = 6;                   // ring units
 constexpr int RMAX = 256;
 constexpr int T_BYTES = (RMAX / 64) * UNIT;          // 64 KB
 constexpr int RING_OFFSET = T_BYTES;
-constexpr int NBUF = 2;
+constexpr int TEAMS = 4;                // epilogue teams of four warps (one per TMEM lane quadrant), 64 output columns each
 constexpr int STAGING_OFFSET = RING_OFFSET + NU * UNIT;
-constexpr int BAR_OFFSET = STAGING_OFFSET + 2 * NBUF * UNIT;
+constexpr int BAR_OFFSET = STAGING_OFFSET + TEAMS * UNIT;
 constexpr int SMEM_TOTAL = BAR_OFFSET + 256 + 1024;
 static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
 }  // namespace fz
@@ -97,8 +97,8 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < NU; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 16); }
-    mbar_init(tready, 16);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 2 * 4 * TEAMS); }
+    mbar_init(tready, 2 * 4 * TEAMS);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_2sm(tmem_ptr, 512);
@@ -201,39 +201,42 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ drain + epilogue (both CTAs, own 128 rows)
-    const int q = (warp - 4) & 3, h = (warp - 4) >> 2;
+    // 16 warps = 4 teams x 4 TMEM lane quadrants; a team owns 64 columns of every 256-column accumulator and one 16 KB
+    // staging buffer, so a chunk costs each warp two tcgen05.ld (issued together), one pass of packing and one TMA store
+    // per team -- the phase-2 MMAs of a chunk take 1.5 us and the epilogue has to keep up with them.
+    const int q = (warp - 4) & 3, team = (warp - 4) >> 2;
     const int r = q * 32 + lane;                                      // row of the CTA's tile = TMEM lane
-    unsigned char* stg_base = smem + STAGING_OFFSET + h * NBUF * UNIT;
+    unsigned char* stg = smem + STAGING_OFFSET + team * UNIT;
     uint32_t use[2] = {0, 0};
-    int nstore = 0;
     const uint32_t tempty0 = mapa_u32(smem_u32(&tempty[0]), 0), tempty1 = mapa_u32(smem_u32(&tempty[1]), 0);
     const uint32_t tready_l = mapa_u32(smem_u32(tready), 0);
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     for (int w = cid; w < sched.items; w += nclusters) {
       int tile, c0, c1;
       fused_item(sched, w, tile, c0, c1);
       const int m0 = tile * (2 * BM) + crank * BM;
-      // ---- drain T: TMEM columns [0, R) -> 16-bit -> shared memory block (col / 64), row r, 16-byte chunk ^ (r & 7)
+      // ---- drain T: TMEM columns [64 team, 64 team + 64) -> 16-bit -> shared-memory block `team`, row r, chunk ^ (r & 7)
       mbar_wait(&tfull[0], use[0] & 1);
       tc_fence_after();
       ++use[0];
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int col = h * 128 + c * 32;
-        if (col < R) {                                                // warp-uniform
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, v);
-          tmem_ld_wait();
-          unsigned char* rowp = smem + (col >> 6) * UNIT + r * 128;
-          const int cc = (col >> 5) & 1;
+      if (team * 64 < R) {                                            // warp-uniform
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_base + (uint32_t)(team * 64), v0);
+        tmem_ld_32x32b_x32(tmem_base + lane_base + (uint32_t)(team * 64 + 32), v1);
+        tmem_ld_wait();
+        unsigned char* rowp = smem + team * UNIT + r * 128;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int chunk = (cc * 4 + j) ^ (r & 7);
-            *reinterpret_cast<uint4*>(rowp + chunk * 16) =
-                make_uint4(pack2f<T>(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
-                           pack2f<T>(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
-                           pack2f<T>(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
-                           pack2f<T>(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
-          }
+        for (int j = 0; j < 4; ++j) {
+          *reinterpret_cast<uint4*>(rowp + ((j ^ (r & 7)) * 16)) =
+              make_uint4(pack2f<T>(__uint_as_float(v0[8 * j]), __uint_as_float(v0[8 * j + 1])),
+                         pack2f<T>(__uint_as_float(v0[8 * j + 2]), __uint_as_float(v0[8 * j + 3])),
+                         pack2f<T>(__uint_as_float(v0[8 * j + 4]), __uint_as_float(v0[8 * j + 5])),
+                         pack2f<T>(__uint_as_float(v0[8 * j + 6]), __uint_as_float(v0[8 * j + 7])));
+          *reinterpret_cast<uint4*>(rowp + (((4 + j) ^ (r & 7)) * 16)) =
+              make_uint4(pack2f<T>(__uint_as_float(v1[8 * j]), __uint_as_float(v1[8 * j + 1])),
+                         pack2f<T>(__uint_as_float(v1[8 * j + 2]), __uint_as_float(v1[8 * j + 3])),
+                         pack2f<T>(__uint_as_float(v1[8 * j + 4]), __uint_as_float(v1[8 * j + 5])),
+                         pack2f<T>(__uint_as_float(v1[8 * j + 6]), __uint_as_float(v1[8 * j + 7])));
         }
       }
       tc_fence_before();
@@ -245,50 +248,46 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 #pragma unroll 1
       for (int c = 0; c < nc; ++c) {
         const int b = ((nc - 1 - c) & 1) ? 0 : 1;
-        const int n0 = (c0 + c) * 256;
+        const int n0 = (c0 + c) * 256 + team * 64;
         mbar_wait(&tfull[b], use[b] & 1);
         tc_fence_after();
         ++use[b];
-#pragma unroll 1
-        for (int sub = 0; sub < 2; ++sub) {
-          unsigned char* stg = stg_base + (nstore % NBUF) * UNIT;
-          ++nstore;
-          if (q == 0 && lane == 0) tma_store_wait_read<NBUF - 1>();
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + h) : "memory");
+        uint32_t v0[32], v1[32];
+        const uint32_t col = (uint32_t)((b ? 256 : 0) + team * 64);
+        tmem_ld_32x32b_x32(tmem_base + lane_base + col, v0);
+        tmem_ld_32x32b_x32(tmem_base + lane_base + col + 32u, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(b ? tempty1 : tempty0);    // accumulator columns of this warp are in registers
+        if (bias) {
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            const int ci = 2 * sub + cc;
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((b ? 256 : 0) + h * 128 + ci * 32), v);
-            tmem_ld_wait();
-            const int col0 = n0 + h * 128 + ci * 32;
-            float f[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            if (bias) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (col0 + j < m) f[j] += to_f32<T>(bias[col0 + j]);
-            }
-            unsigned char* rowp = stg + r * 128;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int chunk = (cc * 4 + j) ^ (r & 7);
-              *reinterpret_cast<uint4*>(rowp + chunk * 16) =
-                  make_uint4(pack2f<T>(f[8 * j], f[8 * j + 1]), pack2f<T>(f[8 * j + 2], f[8 * j + 3]),
-                             pack2f<T>(f[8 * j + 4], f[8 * j + 5]), pack2f<T>(f[8 * j + 6], f[8 * j + 7]));
-            }
+          for (int j = 0; j < 32; ++j) {
+            if (n0 + j < m) v0[j] = __float_as_uint(__uint_as_float(v0[j]) + to_f32<T>(bias[n0 + j]));
+            if (n0 + 32 + j < m) v1[j] = __float_as_uint(__uint_as_float(v1[j]) + to_f32<T>(bias[n0 + 32 + j]));
           }
-          if (sub == 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(b ? tempty1 : tempty0);
-          }
-          fence_proxy_async_smem();
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + h) : "memory");
-          if (q == 0 && lane == 0) {
-            tma_store_2d(&tmY, stg, n0 + h * 128 + sub * 64, m0);
-            tma_store_commit();
-          }
+        }
+        if (q == 0 && lane == 0) tma_store_wait_read<0>();            // the team's previous store has read the buffer
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + team) : "memory");
+        unsigned char* rowp = stg + r * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          *reinterpret_cast<uint4*>(rowp + ((j ^ (r & 7)) * 16)) =
+              make_uint4(pack2f<T>(__uint_as_float(v0[8 * j]), __uint_as_float(v0[8 * j + 1])),
+                         pack2f<T>(__uint_as_float(v0[8 * j + 2]), __uint_as_float(v0[8 * j + 3])),
+                         pack2f<T>(__uint_as_float(v0[8 * j + 4]), __uint_as_float(v0[8 * j + 5])),
+                         pack2f<T>(__uint_as_float(v0[8 * j + 6]), __uint_as_float(v0[8 * j + 7])));
+          *reinterpret_cast<uint4*>(rowp + (((4 + j) ^ (r & 7)) * 16)) =
+              make_uint4(pack2f<T>(__uint_as_float(v1[8 * j]), __uint_as_float(v1[8 * j + 1])),
+                         pack2f<T>(__uint_as_float(v1[8 * j + 2]), __uint_as_float(v1[8 * j + 3])),
+                         pack2f<T>(__uint_as_float(v1[8 * j + 4]), __uint_as_float(v1[8 * j + 5])),
+                         pack2f<T>(__uint_as_float(v1[8 * j + 6]), __uint_as_float(v1[8 * j + 7])));
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + team) : "memory");
+        if (q == 0 && lane == 0) {
+          tma_store_2d(&tmY, stg, n0, m0);
+          tma_store_commit();
         }
       }
     }

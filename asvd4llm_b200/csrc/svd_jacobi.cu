@@ -125,6 +125,7 @@ SvdPlan make_plan(int m, int n, int batch, bool allow_inner) {
   p.off_flag = take(sizeof(int) * (size_t)batch * p.pairs);
   p.off_maxoff = take(sizeof(unsigned) * 2 * (size_t)batch);   // [batch] max cosine bits, [batch] near-converged pair counts
   p.off_done = take(sizeof(int) * (size_t)batch);
+  p.off_prec = take(sizeof(int) * (size_t)batch);      // Gram mode of every matrix (0: single TF32 pass, 1: fp32-accurate split)
   p.off_sigma = take(sizeof(float) * (size_t)batch * p.nv_pad);
   p.off_perm = take(sizeof(int) * (size_t)batch * p.nv_pad);
   p.off_status = take(sizeof(int) * (size_t)batch);
@@ -585,7 +586,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1)
 solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, float* __restrict__ Rout,
              int* __restrict__ pairflag, unsigned* __restrict__ maxoff_bits, int* __restrict__ status,
              const int* __restrict__ done, float tol, int transpose_out, int dbg_steps, const int2* __restrict__ pairs,
-             int* __restrict__ track, int nb, int round_stamp, int precise, int half_gram) {
+             int* __restrict__ track, int nb, int round_stamp, const int* __restrict__ precise_b, int half_gram_tc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* G = reinterpret_cast<float*>(smem_raw);            // [JK][SLD]; later E = R^T R
   float* Rs = G + JK * SLD;                                 // [JK][SLD]; R in sorted column order (after the sweep)
@@ -607,6 +608,7 @@ solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, flo
     if (tid == 0) pairflag[idx] = 0;
     return;
   }
+  const int precise = precise_b[b], half_gram = half_gram_tc && precise;     // Gram mode of THIS matrix (see run_svd)
   if (!solve_prologue(Gpart, chunks, idx, b, pr, tid, G, red, pairflag, maxoff_bits, status, tol, trk, nb, round_stamp,
                       precise, gridDim.y, half_gram))
     return;
@@ -1185,6 +1187,7 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
   int* flag = reinterpret_cast<int*>(ws + p.off_flag);
   unsigned* maxoff = reinterpret_cast<unsigned*>(ws + p.off_maxoff);
   int* done = reinterpret_cast<int*>(ws + p.off_done);
+  int* prec = reinterpret_cast<int*>(ws + p.off_prec);
   float* sigma = reinterpret_cast<float*>(ws + p.off_sigma);
   int* perm = reinterpret_cast<int*>(ws + p.off_perm);
   int* status = reinterpret_cast<int*>(ws + p.off_status);
@@ -1333,13 +1336,21 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
   bool gave_up = false;
   int sweep = 0;
   bool all_done = false;
-  // some pair of a running matrix was already (nearly) orthogonal in an earlier sweep -- or the vectors arrive
-  // pre-conditioned, where the single-pass Gram could not see the cosines that are left
-  bool near_seen = (mode & MODE_SKIP_PREP) != 0;
+  // PER MATRIX: some pair of it was already (nearly) orthogonal in an earlier sweep -- or the vectors arrive
+  // pre-conditioned, where the single-pass Gram could not see the cosines that are left.  Kept per matrix (and handed to
+  // the kernels as an array) so that a weight's arithmetic never depends on which other weights share its batch: the
+  // factors are bitwise the same for every batch size, hence for every world size of a sharded run.
+  std::vector<char> near_seen(p.batch, (mode & MODE_SKIP_PREP) != 0 ? 1 : 0);
+  std::vector<int> h_prec(p.batch, -1), h_prec_new(p.batch, 0);
   for (; sweep < max_sweeps && !all_done; ++sweep) {
-    // single-pass TF32 Gram only while every pair still needs work; afterwards the 3-term split (fp32-accurate),
-    // without which the threshold test could not skip converged pairs nor certify convergence
-    const int gram_precise = (!use_tc || near_seen) ? 1 : 0;
+    // single-pass TF32 Gram only while every pair of the matrix still needs work; afterwards the 3-term split
+    // (fp32-accurate), without which the threshold test could not skip converged pairs nor certify convergence
+    for (int b = 0; b < p.batch; ++b) h_prec_new[b] = (!use_tc || near_seen[b]) ? 1 : 0;
+    if (h_prec_new != h_prec) {
+      h_prec = h_prec_new;
+      ASVD_CUDA_CHECK(cudaMemcpyAsync(prec, h_prec.data(), sizeof(int) * p.batch, cudaMemcpyHostToDevice, st));
+      ASVD_CUDA_CHECK(cudaStreamSynchronize(st));        // pageable source: the vector may change before a deferred copy reads it
+    }
     ASVD_CUDA_CHECK(cudaMemsetAsync(maxoff, 0, sizeof(unsigned) * 2 * p.batch, st));
     if (n_parts == 2) {
       ASVD_CUDA_CHECK(cudaEventRecord(ev_fork, st));
@@ -1348,7 +1359,7 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
     for (int r = 0; r < p.rounds; ++r) {
       const int2* pr = d_pairs + (size_t)r * p.pairs;
       const int round_stamp = 2 + sweep * p.rounds + r;
-      const int half_gram = (use_tc && gram_precise) ? 1 : 0;   // gram_tc_kernel's precise mode stores T, G = T + T^T
+      const int half_gram = use_tc ? 1 : 0;   // gram_tc_kernel's precise mode stores T, G = T + T^T (kernels AND it with prec[b])
       for (int h = 0; h < n_parts; ++h) {
         const Part& q = parts[h];
         cudaStream_t s = q.s;
@@ -1359,9 +1370,10 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
         int* statusq = status + q.b0;
         int* trackq = track + q.b0 * track_stride;
         unsigned* maxoffq = maxoff + 2 * q.b0;
+        const int* precq = prec + q.b0;
         float* Xq = X + q.b0 * xs;
         if (use_tc) {
-          ASVD_LAUNCH(K_GRAM, s, ASVD_CUDA_CHECK(tc::launch_gram_tc(q.tmK, pr, p.pairs, p.chunks, p.chunk_cols, p.len_pad, p.nv_pad, q.nb, Gq, doneq, gram_precise, trackq, s)));
+          ASVD_LAUNCH(K_GRAM, s, ASVD_CUDA_CHECK(tc::launch_gram_tc(q.tmK, pr, p.pairs, p.chunks, p.chunk_cols, p.len_pad, p.nv_pad, q.nb, Gq, doneq, precq, trackq, s)));
         } else {
           ASVD_LAUNCH(K_GRAM, s, (gram_kernel<<<dim3(p.chunks, p.pairs, q.nb), 256, 0, s>>>(Xq, xs, p.len_pad, pr, p.len_pad, p.chunks, p.pairs, Gq, doneq, trackq, p.nb, p.chunk_cols)));
         }
@@ -1369,12 +1381,12 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
         if (n_parts == 2 && !(r == 0 && h == 0)) ASVD_CUDA_CHECK(cudaStreamWaitEvent(s, ev_solve[h ^ 1], 0));
         if (solve_lean) {
           float* auxq = reinterpret_cast<float*>(ws + p.off_aux) + (size_t)q.b0 * p.pairs * QAUX_FLOATS;
-          ASVD_LAUNCH(K_SOLVE, s, (solve_quad_g_kernel<<<dim3(p.pairs, q.nb), 256, SOLVEQG_SMEM, s>>>(Gq, p.chunks, p.pairs, auxq, flagq, maxoffq, statusq, doneq, tol, pr, trackq, p.nb, round_stamp, gram_precise, half_gram)));
+          ASVD_LAUNCH(K_SOLVE, s, (solve_quad_g_kernel<<<dim3(p.pairs, q.nb), 256, SOLVEQG_SMEM, s>>>(Gq, p.chunks, p.pairs, auxq, flagq, maxoffq, statusq, doneq, tol, pr, trackq, p.nb, round_stamp, precq, half_gram)));
           ASVD_LAUNCH(K_SOLVE, s, (solve_quad_r_kernel<<<dim3(p.pairs, q.nb), 256, SOLVEQR_SMEM, s>>>(auxq, p.pairs, Rq, flagq, doneq)));
         } else if (solve_quad)
-          ASVD_LAUNCH(K_SOLVE, s, (solve_quad_kernel<<<dim3(p.pairs, q.nb), SOLVE_THREADS, SOLVEQ_SMEM, s>>>(Gq, p.chunks, p.pairs, Rq, flagq, maxoffq, statusq, doneq, tol, polish_flag, pr, trackq, p.nb, round_stamp, gram_precise, half_gram)));
+          ASVD_LAUNCH(K_SOLVE, s, (solve_quad_kernel<<<dim3(p.pairs, q.nb), SOLVE_THREADS, SOLVEQ_SMEM, s>>>(Gq, p.chunks, p.pairs, Rq, flagq, maxoffq, statusq, doneq, tol, polish_flag, pr, trackq, p.nb, round_stamp, precq, half_gram)));
         else
-          ASVD_LAUNCH(K_SOLVE, s, (solve_kernel<<<dim3(p.pairs, q.nb), SOLVE_THREADS, SOLVE_SMEM, s>>>(Gq, p.chunks, p.pairs, Rq, flagq, maxoffq, statusq, doneq, tol, polish_flag, dbg_steps, pr, trackq, p.nb, round_stamp, gram_precise, half_gram)));
+          ASVD_LAUNCH(K_SOLVE, s, (solve_kernel<<<dim3(p.pairs, q.nb), SOLVE_THREADS, SOLVE_SMEM, s>>>(Gq, p.chunks, p.pairs, Rq, flagq, maxoffq, statusq, doneq, tol, polish_flag, dbg_steps, pr, trackq, p.nb, round_stamp, precq, half_gram)));
         if (n_parts == 2) ASVD_CUDA_CHECK(cudaEventRecord(ev_solve[h], s));
         if (use_tc) {
           ASVD_LAUNCH(K_UPDATE, s, ASVD_CUDA_CHECK(tc::launch_update_tc(q.tmMN, Xq, xs, p.len_pad, pr, p.pairs, p.nv_pad, p.len_pad, q.nb, Rq, flagq, doneq, s)));
@@ -1407,7 +1419,7 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
       // fp32 plateau of 2-4e-6, so a sweep that started below tol_pre leaves the vectors orthogonal to ~2e-5 or
       // better; asking for a further verification sweep below `tol` (which sits ON that plateau) costs one to two
       // sweeps and changes sigma by < 1e-5 relative.
-      bool finished = mo < tol_pre && gram_precise;
+      bool finished = mo < tol_pre && h_prec[b];
       if ((mode & MODE_STOP_AT_VECTORS) && !finished) {
         // pre-conditioning stage: the square problem runs on the SQUARED spectrum; on ill-conditioned weights its fp32
         // cosines never settle.  The largest cosine is no guide (it RISES for a dozen sweeps on a healthy problem while
@@ -1427,11 +1439,13 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
       else { all_done = false; worst = fmaxf(worst, mo); best = fminf(best, mo); }
       // ASVD_B200_NEAR_PCT (experiments): stay with the single-pass Gram until that percentage of a matrix's block pairs
       // is below 1e-2 (default 0: the first such pair switches to the precise Gram)
-      if (h_maxoff[near_idx(b)] > near_min) near_seen = true;
+      if (h_maxoff[near_idx(b)] > near_min) near_seen[b] = 1;
     }
     (void)worst; (void)best;
     if (getenv("ASVD_B200_TRACE")) {                 // diagnostic: convergence trace, one line per sweep
-      fprintf(stderr, "sweep %2d precise %d  max|cos|:", sweep + 1, gram_precise);
+      fprintf(stderr, "sweep %2d precise", sweep + 1);
+      for (int b = 0; b < p.batch; ++b) fprintf(stderr, " %d", h_prec[b]);
+      fprintf(stderr, "  max|cos|:");
       for (int b = 0; b < p.batch; ++b) { float mo; memcpy(&mo, &h_maxoff[cos_idx(b)], 4); fprintf(stderr, " %.3e", mo); }
       fprintf(stderr, "  near-orthogonal pairs:");
       for (int b = 0; b < p.batch; ++b) fprintf(stderr, " %u", h_maxoff[near_idx(b)]);

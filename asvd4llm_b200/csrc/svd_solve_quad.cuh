@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1)
 solve_quad_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, float* __restrict__ Rout,
                   int* __restrict__ pairflag, unsigned* __restrict__ maxoff_bits, int* __restrict__ status,
                   const int* __restrict__ done, float tol, int transpose_out, const int2* __restrict__ pairs,
-                  int* __restrict__ track, int nb, int round_stamp, int precise, int half_gram) {
+                  int* __restrict__ track, int nb, int round_stamp, const int* __restrict__ precise_b, int half_gram_tc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* G = reinterpret_cast<float*>(smem_raw);            // [JK][SLD] summed Gram; staging of the G threads; later E
   float* Rs = G + JK * SLD;                                 // [JK][SLD] staging of the R threads; then R, sorted columns
@@ -288,6 +288,7 @@ solve_quad_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat
   }
   if (tid < QSTEPS + 1) tc::mbar_init(&mb[tid], 1);         // ordered before their first use by the prologue's barriers
   for (int i = tid; i < (QROUNDS - 1) * 32; i += SOLVE_THREADS) qsrc[i] = c_quad_src[i];
+  const int precise = precise_b[b], half_gram = half_gram_tc && precise;     // Gram mode of THIS matrix (see run_svd)
   if (!solve_prologue(Gpart, chunks, idx, b, pr, tid, G, red, pairflag, maxoff_bits, status, tol, trk, nb, round_stamp,
                       precise, gridDim.y, half_gram))
     return;
@@ -463,7 +464,7 @@ __global__ void __launch_bounds__(256, 2)
 solve_quad_g_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, float* __restrict__ aux,
                     int* __restrict__ pairflag, unsigned* __restrict__ maxoff_bits, int* __restrict__ status,
                     const int* __restrict__ done, float tol, const int2* __restrict__ pairs, int* __restrict__ track, int nb,
-                    int round_stamp, int precise, int half_gram) {
+                    int round_stamp, const int* __restrict__ precise_b, int half_gram_tc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* G = reinterpret_cast<float*>(smem_raw);            // [JK][SLD] summed Gram, then the staging area of the moves
   float2* csh = reinterpret_cast<float2*>(G + JK * SLD);    // [QRING][64] rotations of the last steps
@@ -484,6 +485,7 @@ solve_quad_g_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_m
     return;
   }
   for (int i = tid; i < (QROUNDS - 1) * 32; i += 256) qsrc[i] = c_quad_src[i];
+  const int precise = precise_b[b], half_gram = half_gram_tc && precise;
   if (!solve_prologue<256>(Gpart, chunks, idx, b, pr, tid, G, red, pairflag, maxoff_bits, status, tol, trk, nb, round_stamp,
                            precise, gridDim.y, half_gram))
     return;

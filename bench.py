@@ -410,6 +410,24 @@ def svd_workload(ctx):
                     "class_ms_first_2_sweeps": {k: round(v["ms"], 3) for k, v in classes.items()},
                     "class_ms_full_factorisation": full_run}
 
+    # ---- the same shape with a decaying spectrum (trained, activation-scaled weights look like this; the Gaussian input
+    # above has a clustered Marchenko-Pastur bulk, the slowest case for a Jacobi method): sweeps and time, rank 0
+    decaying = None
+    if rank == 0:
+        gd = torch.Generator(device=dev).manual_seed(99)
+        Wd = []
+        for _ in range(B):
+            u = torch.randn(M, 64, device=dev, generator=gd); v = torch.randn(64, N_IN, device=dev, generator=gd)
+            sv = torch.logspace(0, -2, 64, device=dev) * 8.0
+            Wd.append(((torch.randn(M, N_IN, device=dev, generator=gd) + (u * sv) @ v) * 0.02).half())
+        sc = [_lib.scaling_vector(s, None, ALPHA, N_IN, dev) for s in pools[0][1]]
+        f2 = _lib.scaled_svd(Wd, sc); torch.cuda.synchronize()
+        t0 = time.perf_counter(); f2 = _lib.scaled_svd(Wd, sc); torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        decaying = {"input": "Gaussian bulk + 64 directions with singular values decaying over two decades", "sweeps": list(f2.sweeps),
+                    "ms_per_matrix": round(dt * 1e3 / B, 2), "matrices_per_s": round(B / dt, 2)}
+        del Wd, f2
+
     # ---- baselines on this box, rank 0, N=1 only: the reference's algorithms on the host cores (bounded sample) and on
     # the same GPU through torch (the kernel to beat is the vendor library on the same box)
     cpu_baseline = None
@@ -424,7 +442,8 @@ def svd_workload(ctx):
                        batch_rule="_lib.suggest_batch(4096, 4096): the batch binary_search's final pass uses for this shape",
                        l2=f"inputs larger than L2: {B} x 128 MB fp32 working set per step vs 126 MB L2; two input sets alternate",
                        parallelism=f"{world} independent ranks, disjoint weights, no data-path collective",
-                       step_ms=[round(t, 1) for t in per_step], extra_untimed_warmup_steps=extra, hiccup=hiccup),
+                       step_ms=[round(t, 1) for t in per_step], extra_untimed_warmup_steps=extra, hiccup=hiccup,
+                       decaying_spectrum_input=decaying),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
