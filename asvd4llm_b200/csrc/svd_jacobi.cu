@@ -1373,7 +1373,13 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
         const int* precq = prec + q.b0;
         float* Xq = X + q.b0 * xs;
         if (use_tc) {
-          ASVD_LAUNCH(K_GRAM, s, ASVD_CUDA_CHECK(tc::launch_gram_tc(q.tmK, pr, p.pairs, p.chunks, p.chunk_cols, p.len_pad, p.nv_pad, q.nb, Gq, doneq, precq, trackq, s)));
+          // one launch per Gram mode present among the part's running matrices (usually one)
+          bool any_mode[2] = {false, false};
+          for (int b = q.b0; b < q.b0 + q.nb; ++b)
+            if (!h_done[b]) any_mode[h_prec[b] ? 1 : 0] = true;
+          for (int md = 0; md < 2; ++md)
+            if (any_mode[md])
+              ASVD_LAUNCH(K_GRAM, s, ASVD_CUDA_CHECK(tc::launch_gram_tc(q.tmK, pr, p.pairs, p.chunks, p.chunk_cols, p.len_pad, p.nv_pad, q.nb, Gq, doneq, md, precq, trackq, s)));
         } else {
           ASVD_LAUNCH(K_GRAM, s, (gram_kernel<<<dim3(p.chunks, p.pairs, q.nb), 256, 0, s>>>(Xq, xs, p.len_pad, pr, p.len_pad, p.chunks, p.pairs, Gq, doneq, trackq, p.nb, p.chunk_cols)));
         }

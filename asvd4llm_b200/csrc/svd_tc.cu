@@ -53,13 +53,15 @@ __device__ __forceinline__ void split_tile(float4* hi, float4* lo, int t) {
   }
 }
 
+// One launch serves the matrices whose mode precise_b[b] equals `precise` (the mode is a per-matrix state, so that a
+// weight's arithmetic never depends on its batch-mates; a round of a batch in transition is two launches).
 // precise = 1: 3-term split (fp32-accurate Gram).  precise = 0: one TF32 pass on the raw tile (the MMA ignores the low
 // mantissa bits); used while the off-diagonal cosines are still >= 1e-2, where 1e-3 relative accuracy of G only
 // perturbs the rotation angles (R stays exactly orthogonal, so nothing is lost but a little convergence speed).
 __global__ void __launch_bounds__(GR_THREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__ pairs, int pairs_per_mat, int chunks,
                int chunk_cols, int len_pad, int nv_pad, int n_items, float* __restrict__ Gpart,
-               const int* __restrict__ done, const int* __restrict__ precise_b, const int* __restrict__ track) {
+               const int* __restrict__ done, int precise, const int* __restrict__ precise_b, const int* __restrict__ track) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + GR_BAR_OFFSET);   // [NH] TMA landed
@@ -90,7 +92,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__
       int hs = 0; uint32_t hph = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int b = item / per_mat, p = (item % per_mat) / chunks, c = item % chunks;
-        if (done[b]) continue;
+        if (done[b] || precise_b[b] != precise) continue;   // the launch serves the matrices in ITS Gram mode
         const int2 pr = pairs[p];
         if (pair_is_clean(track, nv_pad / JB, b, pr.x, pr.y)) continue;
         const int k0 = c * chunk_cols, k1 = min(len_pad, k0 + chunk_cols);
@@ -115,9 +117,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int b = item / per_mat, c = item % chunks;
-      if (done[b]) continue;
+      if (done[b] || precise_b[b] != precise) continue;   // the launch serves the matrices in ITS Gram mode
       { const int2 pr = pairs[(item % per_mat) / chunks]; if (pair_is_clean(track, nv_pad / JB, b, pr.x, pr.y)) continue; }
-      const int precise = precise_b[b];            // per MATRIX: a weight's arithmetic never depends on its batch-mates
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       ++it;
@@ -161,7 +162,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int b = item / per_mat;
-      if (done[b]) continue;
+      if (done[b] || precise_b[b] != precise) continue;   // the launch serves the matrices in ITS Gram mode
       { const int2 pr = pairs[(item % per_mat) / chunks]; if (pair_is_clean(track, nv_pad / JB, b, pr.x, pr.y)) continue; }
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
@@ -184,23 +185,16 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && precise) {
     const int t = threadIdx.x - 256;                         // row of the tile = TMEM lane; warp 8+q owns lanes 32q..
     const int q = warp - 8;
     int hs = 0; uint32_t hph = 0;
     int as = 0; uint32_t aph = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int b = item / per_mat, c = item % chunks;
-      if (done[b]) continue;
+      if (done[b] || precise_b[b] != precise) continue;   // the launch serves the matrices in ITS Gram mode
       { const int2 pr = pairs[(item % per_mat) / chunks]; if (pair_is_clean(track, nv_pad / JB, b, pr.x, pr.y)) continue; }
       const int k0 = c * chunk_cols, k1 = min(len_pad, k0 + chunk_cols);
-      if (!precise_b[b]) {
-        // single-pass item: the MMA warp consumes the landed tiles itself; only keep the stage counter in step
-        const int n = (k1 - k0 + 31) >> 5, tot = hs + n;
-        hph ^= (uint32_t)((tot / GR_NH) & 1);
-        hs = tot % GR_NH;
-        continue;
-      }
       for (int k = k0; k < k1; k += 32) {
         mbar_wait(&full[hs], hph);
         // row t of the 128-byte-swizzled tile: 16-byte chunk j lives at chunk j ^ (t & 7)
@@ -482,7 +476,8 @@ bool make_x_tmap(CUtensorMap* map, const float* X, int batch, int nv_pad, int le
 }
 
 cudaError_t launch_gram_tc(const CUtensorMap& tmX, const int2* pairs, int pairs_per_mat, int chunks, int chunk_cols,
-                           int len_pad, int nv_pad, int batch, float* Gpart, const int* done, const int* precise_b, const int* track, cudaStream_t st) {
+                           int len_pad, int nv_pad, int batch, float* Gpart, const int* done, int precise, const int* precise_b, const int* track,
+                           cudaStream_t st) {
   static bool attr[ASVD_MAX_DEVICES] = {};
   const int dev = current_device_slot();
   if (!attr[dev]) {
@@ -493,7 +488,7 @@ cudaError_t launch_gram_tc(const CUtensorMap& tmX, const int2* pairs, int pairs_
   const int n_items = batch * pairs_per_mat * chunks;
   const int grid = n_items < sm_count() ? n_items : sm_count();
   gram_tc_kernel<<<grid, GR_THREADS, GR_SMEM, st>>>(tmX, pairs, pairs_per_mat, chunks, chunk_cols, len_pad, nv_pad, n_items,
-                                                    Gpart, done, precise_b, track);
+                                                    Gpart, done, precise, precise_b, track);
   return cudaGetLastError();
 }
 

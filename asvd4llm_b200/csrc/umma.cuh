@@ -219,6 +219,14 @@ __device__ __forceinline__ void mma_f16_ss_2sm(uint32_t d_tmem, uint64_t adesc, 
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from tensor memory (each CTA's own 128 lanes; 16-bit elements packed two per 32-bit column), B from shared memory
+__device__ __forceinline__ void mma_f16_ts_2sm(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // all prior MMAs of the pair -> one arrival on the barrier at this offset in every CTA of cta_mask
 __device__ __forceinline__ void tc_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(

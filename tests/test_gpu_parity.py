@@ -886,3 +886,29 @@ def test_sharded_final_pass_is_bitwise_independent_of_world_size():
             assert ncoll == (0 if world == 1 else 2)
     assert len(results[(1, 0)]) == 14                               # 15 linears, one kept raw
     assert results[(2, 0)] == results[(1, 0)] and results[(2, 1)] == results[(1, 0)]
+
+
+def test_mixed_convergence_batch_is_bitwise_independent():
+    """Weights that reach the precise Gram mode in different sweeps (a Gaussian bulk, a decaying spectrum, an almost
+    orthogonal matrix, a rank-deficient one) share one batch: every matrix must come out bitwise as when it is factorised
+    alone -- the Gram mode is per-matrix state, a round of a batch in transition runs one Gram launch per mode."""
+    L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n = 1024
+    Ws = []
+    Ws.append((torch.randn(n, n, device="cuda", generator=g) * 0.02).half())
+    u = torch.randn(n, 64, device="cuda", generator=g); v = torch.randn(64, n, device="cuda", generator=g)
+    Ws.append(((torch.randn(n, n, device="cuda", generator=g) + (u * torch.logspace(0, -2, 64, device="cuda") * 8) @ v) * 0.02).half())
+    Q = torch.linalg.qr(torch.randn(n, n, device="cuda", generator=g)).Q
+    Ws.append((Q * torch.linspace(1.0, 0.1, n, device="cuda")).half())
+    Ws.append((torch.randn(n, 100, device="cuda", generator=g) @ torch.randn(100, n, device="cuda", generator=g) * 0.01).half())
+    Ws.append((torch.randn(n, n, device="cuda", generator=g) * 0.02).half())
+    scales = [L.scaling_vector(torch.exp(torch.randn(n, device="cuda", generator=g)).half(), None, 0.5, n, "cuda") for _ in Ws]
+    fact = L.scaled_svd(Ws, scales)
+    assert len(set(fact.sweeps)) > 1, fact.sweeps                      # they really do converge at different times
+    for b in range(len(Ws)):
+        single = L.scaled_svd([Ws[b]], [scales[b]])
+        assert torch.equal(single.sigma(0), fact.sigma(b)), b
+        A1, B1 = single.extract(400, "UV", torch.float16, 0)
+        A2, B2 = fact.extract(400, "UV", torch.float16, b)
+        assert torch.equal(A1, A2) and torch.equal(B1, B2), b
