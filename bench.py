@@ -49,14 +49,18 @@ def peaks():
 
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi polling in a child process, started BEFORE the warm-up (its NVML start-up takes most of a second and was
+    seen to stall a launch-heavy step when it fell inside the timed region); only the samples whose timestamps lie between
+    begin() and end() are reported."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.proc, self.index = None, index
+        self.t0 = self.t1 = None
         self.result = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
 
-    def __enter__(self):
+    def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -65,31 +69,55 @@ class ClockSampler:
             self.proc = None
         return self
 
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
+
+    # context-manager form: the whole `with` body is the sampled region (workloads without a separate warm-up phase)
+    def __enter__(self):
+        self.start()
+        time.sleep(1.0)                     # let NVML come up before the region starts
+        self.begin()
+        return self
+
     def __exit__(self, *a):
+        self.end()
+        self.stop()
+
+    def stop(self):
         if self.proc is None:
-            return
+            return self.result
+        if self.t1 is None:
+            self.end()
         time.sleep(0.15)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except Exception:
             self.proc.kill()
-            return
+            return self.result
+        import datetime
         sm, mx, reasons = [], [], set()
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if self.t0 is not None and not (self.t0 - 0.05 <= ts <= self.t1 + 0.05):
+                    continue
+                sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         if sm:
             self.result = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
                            "samples": len(sm)}
+        return self.result
 
 
 # ---------------------------------------------------------------------------------------------------------------- CPU arm
@@ -278,6 +306,7 @@ def svd_workload(ctx):
         outs = [fact.extract(r, "UV", torch.float16, b) for b in range(B)]
         return fact, outs
 
+    clocks = ClockSampler(ctx.local).start()             # NVML start-up happens during the warm-up, not the timed region
     for i in range(args.warmup):
         fact, _ = device_step(i)
     ctx.barrier()
@@ -301,15 +330,17 @@ def svd_workload(ctx):
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    with ClockSampler(ctx.local) as clocks:
-        ctx.barrier()
-        e0.record()
-        marks[0].record()
-        for i in range(args.steps):
-            fact, outs = device_step(i)
-            marks[i + 1].record()
-        e1.record()
-        ctx.barrier()
+    ctx.barrier()
+    clocks.begin()
+    e0.record()
+    marks[0].record()
+    for i in range(args.steps):
+        fact, outs = device_step(i)
+        marks[i + 1].record()
+    e1.record()
+    ctx.barrier()
+    clocks.end()
+    clocks.stop()
     per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]
     ms = ctx.max_over_ranks(e0.elapsed_time(e1))
     launches = _lib.launch_count() - launches0
