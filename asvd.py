@@ -98,7 +98,8 @@ def main(args):
             chosen, default = search_allocation(model, sensitivity, calib_loader, args, index=index)
             stats = sharding.decompose_sharded(model, chosen, default, args, index=index)
             if rank == 0:
-                print(f"sharded final pass: decompose {stats['decompose_s']:.2f} s, factor exchange {stats['exchange_s']:.2f} s "
+                print(f"sharded final pass: decompose {stats['decompose_s']:.2f} s, wait for the slowest rank {stats['imbalance_wait_s']:.2f} s, "
+                      f"factor exchange {stats['exchange_s']:.2f} s "
                       f"({stats['bytes'] / 1e9:.2f} GB received in {stats['collectives']} collectives)")
         if args.weight_quant != "none":
             print("weight quantization is out of scope of the B200 path; skipped")

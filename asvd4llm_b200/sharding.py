@@ -178,7 +178,8 @@ def broadcast_factors(model: nn.Module, owners: Dict[str, int], replaced: Iterab
 
 def decompose_sharded(model: nn.Module, chosen: Dict[str, float], default_ratio, args, index=None) -> Dict[str, float]:
     """binary_search.py:112-128 with the layers split over the ranks by LPT (cost model layer_cost), followed by the
-    factor exchange.  Returns the exchange statistics plus the seconds spent in each part (device-synchronised)."""
+    factor exchange.  Returns the exchange statistics plus the seconds spent in each part (device-synchronised): this rank's own
+    decomposition, its wait for the slowest owner, the exchange proper."""
     import time
     from .binary_search import decompose_layers, LinearIndex
     rank, world = _world()
@@ -188,10 +189,14 @@ def decompose_sharded(model: nn.Module, chosen: Dict[str, float], default_ratio,
     sync(); t0 = time.perf_counter()
     decompose_layers(model, chosen, default_ratio, args, layer_filter=lambda full: owners[full] == rank, index=index)
     sync(); t1 = time.perf_counter()
+    if world > 1:
+        dist.barrier()                   # so that a rank's wait for the slowest owner is not booked as exchange time
+        sync()
+    t2 = time.perf_counter()
     replaced = [full for full, ratio in chosen.items() if ratio != default_ratio]
     stats = broadcast_factors(model, owners, replaced)
-    sync(); t2 = time.perf_counter()
-    stats.update(decompose_s=t1 - t0, exchange_s=t2 - t1)
+    sync(); t3 = time.perf_counter()
+    stats.update(decompose_s=t1 - t0, imbalance_wait_s=t2 - t1, exchange_s=t3 - t2)
     return stats
 
 

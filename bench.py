@@ -36,6 +36,7 @@ METRIC = "weight-matrices factorised/sec (full-model ASVD wall-clock) at 1/2/4/8
 UNIT = "matrices/s"
 WORKLOAD = "single 4096x4096 fp16 weight: activation-scaled SVD + rank-1843 truncation (param_ratio 0.9, alpha 0.5, sigma_fuse UV)"
 FWD_WORKLOAD = "SVDLinear.forward: B=32 L=2048 d=4096 fp16, rank r in {256, 512, 1024, 1843}"
+FWD_CONFIG = {"workload": FWD_WORKLOAD, "l2": "x and y are 512 MB each: larger than the 126 MB L2"}
 LLAMA_WORKLOAD = "Llama-2-7B shapes (225 linears, random init) full ASVD factorisation at param_ratio 0.9, layers sharded over the ranks, factors exchanged"
 
 
@@ -147,8 +148,11 @@ def _host_threads() -> int:
 
 
 def svd_config(batch, rank):
-    """The keys both arms print for the svd workload (the driver compares the two configs)."""
-    return {"workload": WORKLOAD, "batch_per_step_per_gpu": batch, "rank": rank}
+    """`config` of the svd workload: the SAME dict in both arms (the driver compares the two); everything that depends on
+    the run (sweeps, per-step times, ...) goes to the line's `run` key instead."""
+    return {"workload": WORKLOAD, "batch_per_step_per_gpu": batch, "rank": rank,
+            "l2": f"inputs larger than L2: {batch} x 128 MB fp32 working set per step vs 126 MB L2; two input sets alternate",
+            "parallelism": "independent ranks, disjoint weights, no data-path collective"}
 
 
 def run_reference(args, rank, world):
@@ -177,7 +181,7 @@ def run_reference(args, rank, world):
         _emit({"impl": "reference", "metric": "SVDLinear.forward throughput (mean over the four ranks)", "value": value, "unit": "tokens/s",
                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot * 1e3, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": {"workload": FWD_WORKLOAD},
+               "config": FWD_CONFIG,
                "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": cores, "kind": "port",
                                 "sample": "one 2048-token sequence per rank r, fp32 F.linear pair (upstream's forward) on the host"},
                "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
@@ -206,7 +210,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(svd_config(_default_batch_static(), 1843), where="host CPU, oracle port of the upstream algorithm; one weight per CPU step"),
+        "config": svd_config(_default_batch_static(), 1843),
+        "run": {"where": "host CPU, oracle port of the upstream algorithm; one weight per CPU step (a bounded sample of the GPU arm's batch)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -469,12 +474,11 @@ def svd_workload(ctx):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": dict(svd_config(B, r), sweeps=sweeps,
-                       batch_rule="_lib.suggest_batch(4096, 4096): the batch binary_search's final pass uses for this shape",
-                       l2=f"inputs larger than L2: {B} x 128 MB fp32 working set per step vs 126 MB L2; two input sets alternate",
-                       parallelism=f"{world} independent ranks, disjoint weights, no data-path collective",
-                       step_ms=[round(t, 1) for t in per_step], extra_untimed_warmup_steps=extra, hiccup=hiccup,
-                       decaying_spectrum_input=decaying),
+        "config": svd_config(B, r),
+        "run": dict(sweeps=sweeps, ranks=world,
+                    batch_rule="_lib.suggest_batch(4096, 4096): the batch binary_search's final pass uses for this shape",
+                    step_ms=[round(t, 1) for t in per_step], extra_untimed_warmup_steps=extra, hiccup=hiccup,
+                    decaying_spectrum_input=decaying),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -612,6 +616,7 @@ def llama_workload(ctx, n_blocks=32):
     ctx.barrier()
     total = ctx.max_over_ranks(time.perf_counter() - t0)
     dec = ctx.max_over_ranks(stats["decompose_s"])
+    dec_min = -ctx.max_over_ranks(-stats["decompose_s"])
     exch = ctx.max_over_ranks(stats["exchange_s"])
     mods = [mod for _, mod in model.named_modules() if isinstance(mod, SVDLinear)]
     assert len(mods) == len(names), (len(mods), len(names))
@@ -626,7 +631,7 @@ def llama_workload(ctx, n_blocks=32):
         ctx.dist.all_reduce(lo, op=ctx.dist.ReduceOp.MIN); ctx.dist.all_reduce(hi, op=ctx.dist.ReduceOp.MAX)
         assert int(lo.item()) == int(hi.item()), "ranks hold different factors after the exchange"
     return {"linears": len(names), "seconds": round(total, 3), "matrices_per_s": round(len(names) / total, 2),
-            "decompose_s": round(dec, 3), "exchange_s": round(exch, 3),
+            "decompose_s": round(dec, 3), "decompose_s_fastest_rank": round(dec_min, 3), "exchange_s": round(exch, 3),
             "exchange_GB_received_per_rank": round(stats["bytes"] / 1e9, 3), "exchange_collectives": stats["collectives"],
             "exchange_GBps_per_rank": (round(stats["bytes"] / 1e9 / exch, 1) if exch > 0 and stats["bytes"] else None),
             "factors_checksum": chk, "ranks": ctx.world,
@@ -688,7 +693,7 @@ def main():
             _emit({"metric": "SVDLinear.forward throughput (mean over the four ranks)", "value": value, "unit": "tokens/s",
                    "n_gpus": ctx.world, "steps": K, "warmup": W, "ms_per_step": tot_us / 1e3, "higher_is_better": True, "scaling": "weak",
                    "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-                   "config": {"workload": FWD_WORKLOAD, "l2": "x and y are 512 MB each: larger than the 126 MB L2", "per_rank": res},
+                   "config": FWD_CONFIG, "run": {"per_rank": res},
                    "roofline": {"bound": "tensor", "achieved": fl / tot_us / 1e6, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                                 "frac": fl / tot_us / 1e6 / pk["bf16_tflops"], "traffic": None,
                                 "peak_source": pk["source"] + ", bf16_tflops (burst: kernels timed alone)",
@@ -712,7 +717,7 @@ def main():
                                  + json.dumps(per_shape)}
             _emit({"metric": METRIC, "value": res["matrices_per_s"], "unit": UNIT, "n_gpus": ctx.world, "steps": 1, "warmup": 0,
                    "ms_per_step": res["seconds"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                   "dtype": "f32", "data": "synthetic", "config": dict({"workload": LLAMA_WORKLOAD}, **res),
+                   "dtype": "f32", "data": "synthetic", "config": {"workload": LLAMA_WORKLOAD}, "run": res,
                    "roofline": None, "cpu_baseline": cpu,
                    "e2e": {"value": res["matrices_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                            "note": "weights live on the GPU as in upstream's GPU runs; the exchange is inside the timed region"},

@@ -21,6 +21,10 @@ def test_reference_arm_prints_one_json_line_with_all_host_threads():
     assert cb["kind"] == "port" and cb["value"] == d["value"] and "4096x4096" in cb["sample"]
     assert cb["cores"] == len(os.sched_getaffinity(0))     # not the single thread OMP_NUM_THREADS=1 asks for
     assert "workload" in d["config"] and "model" not in d["config"]
+    # the GPU arm prints the same `config` dict (bench.svd_config); run-dependent details live under `run`
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.svd_config(bench._default_batch_static(), 1843)
 
 
 def test_non_zero_ranks_of_the_reference_arm_exit_quietly():
