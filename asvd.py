@@ -70,13 +70,25 @@ def main(args):
     rank = int(os.environ.get("RANK", 0))
     os.makedirs("cache", exist_ok=True)
 
+    import time
+    phase = {}
+
+    def tick(name, t0):
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        phase[name] = round(time.time() - t0, 2)
+
     model, tokenizer = build_model(args, device)
     if not args.raw_model:
         calib_loader = get_calib_data(args, tokenizer, model.config.vocab_size)
+        t0 = time.time()
         if "fisher" in args.scaling_method:
             calib_fisher_info(model, calib_loader, args.use_cache)
         if "abs" in args.scaling_method:
             calib_input_distribution(model, calib_loader, args.scaling_method, args.use_cache)
+        tick("calibration_s", t0)
+        t0 = time.time()
         if args.sensitivity_metric == "stable_rank":
             # one sigma-only factorisation per linear (no model forwards): every rank computes the whole table
             sensitivity = calib_sensitivity_stable_rank(model, calib_loader, args, args.use_cache)
@@ -90,9 +102,13 @@ def main(args):
             sensitivity = calib_sensitivity_ppl(model, calib_loader, args, args.use_cache)
             binary_search_truncation_rank(model, sensitivity, calib_loader, args)
         else:
-            # (layer, ratio) units dealt round-robin: the sweep is almost entirely model forwards (one SVD serves a
-            # layer's six ratios), so equal unit counts are equal work
-            shard = calib_sensitivity_ppl(model, calib_loader, args, args.use_cache, unit_filter=lambda u: u % world == rank)
+            # (layer, ratio) units in contiguous ranges: equal unit counts are equal work (the sweep is almost entirely
+            # model forwards) and a layer's six ratios stay on one rank, which computes its SVD once -- only the
+            # world - 1 layers that straddle a boundary are factorised twice
+            from asvd4llm_b200.sensitivity import enumerate_linears, RATIOS, KV_RATIOS
+            n_units = len(enumerate_linears(model)) * len(KV_RATIOS if args.compress_kv_cache else RATIOS)
+            lo, hi = rank * n_units // world, (rank + 1) * n_units // world
+            shard = calib_sensitivity_ppl(model, calib_loader, args, args.use_cache, unit_filter=lambda u: lo <= u < hi)
             sensitivity = sharding.gather_sensitivity(model, shard)
             index = LinearIndex(model)
             chosen, default = search_allocation(model, sensitivity, calib_loader, args, index=index)
@@ -101,6 +117,9 @@ def main(args):
                 print(f"sharded final pass: decompose {stats['decompose_s']:.2f} s, wait for the slowest rank {stats['imbalance_wait_s']:.2f} s, "
                       f"factor exchange {stats['exchange_s']:.2f} s "
                       f"({stats['bytes'] / 1e9:.2f} GB received in {stats['collectives']} collectives)")
+        tick("sensitivity_search_decompose_s", t0)
+        if rank == 0:
+            print(f"phase times on {world} GPU(s): {phase}")
         if args.weight_quant != "none":
             print("weight quantization is out of scope of the B200 path; skipped")
     if rank == 0:

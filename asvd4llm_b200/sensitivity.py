@@ -41,7 +41,7 @@ def calib_sensitivity_ppl(model, calib_loader, args, use_cache=True, layer_filte
         (layer, ratio) sweep order -- restrict the sweep to a shard; the multi-GPU driver merges the shards
         (asvd4llm_b200.sharding.gather_sensitivity).  With one SVD serving the six ratios of a layer the sweep is > 95 %
         model forwards, so (layer, ratio) units balance the ranks better than layers at the cost of one extra SVD per
-        rank that shares a layer;
+        rank that shares a layer (asvd.py deals contiguous unit ranges, so only world - 1 layers are shared);
       * args.eval_batch_size (asvd.py --eval_batch_size): calibration samples per model forward in evaluate_perplexity
         (upstream: 1).  Same per-sample losses up to floating-point reassociation inside the batched GEMMs."""
     cache_file = sensitivity_cache_file(model, args)
