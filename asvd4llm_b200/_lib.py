@@ -23,7 +23,7 @@ _DTYPES = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 EXPORTS = [
     "asvd_version", "asvd_last_error", "asvd_rank_for_ratio", "asvd_scaling_vector", "asvd_svd_workspace_bytes",
     "asvd_scaled_svd", "asvd_svd_sigma", "asvd_svd_extract", "asvd_lowrank_forward_scratch_bytes",
-    "asvd_lowrank_forward", "asvd_absstat_scratch_bytes", "asvd_absstat_accum",
+    "asvd_lowrank_forward", "asvd_absstat_scratch_bytes", "asvd_absstat_accum", "asvd_linear_forward_stat",
     "asvd_profile_enable", "asvd_profile_read", "asvd_launch_count",
 ]
 KERNEL_CLASSES = ["prep", "gram", "solve", "update", "finalize", "extract", "forward", "absstat"]
@@ -74,6 +74,8 @@ def load() -> C.CDLL:
         lib.asvd_absstat_scratch_bytes.argtypes = [i32]
         lib.asvd_absstat_accum.restype = i32
         lib.asvd_absstat_accum.argtypes = [vp, i64, i64, i32, i32, i32, vp, vp, sz, vp]
+        lib.asvd_linear_forward_stat.restype = i32
+        lib.asvd_linear_forward_stat.argtypes = [vp, i64, i64, i32, vp, i64, i32, vp, vp, i64, i32, i32, vp, vp, sz, vp]
         lib.asvd_profile_enable.restype = None
         lib.asvd_profile_enable.argtypes = [i32]
         lib.asvd_profile_read.restype = i32
@@ -324,6 +326,42 @@ def absstat_accum(x: torch.Tensor, acc: torch.Tensor, method: str) -> None:
     with torch.cuda.device(x.device):
         _check(lib.asvd_absstat_accum(x2.data_ptr(), x2.stride(0), x2.shape[0], n, dtype_code(x.dtype), mode,
                                       acc.data_ptr(), scratch.data_ptr(), nbytes, _stream()))
+
+
+def linear_stat_eligible(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> bool:
+    """Can asvd_linear_forward_stat take this layer call?  16-bit CUDA tensors of one dtype, rows 16-byte aligned."""
+    if not (x.is_cuda and weight.is_cuda and x.dtype in (torch.float16, torch.bfloat16) and weight.dtype == x.dtype):
+        return False
+    if bias is not None and (bias.dtype != x.dtype or not bias.is_cuda):
+        return False
+    m, n = weight.shape
+    return (n % 8 == 0 and m % 8 == 0 and weight.stride(1) == 1 and weight.stride(0) % 8 == 0 and weight.data_ptr() % 16 == 0
+            and x.shape[-1] == n and x.numel() > 0)
+
+
+def linear_forward_stat(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], acc: torch.Tensor,
+                        method: str) -> torch.Tensor:
+    """One calibration step of one nn.Linear in one kernel: y = x W^T + bias, and acc [n] updated from |x| exactly as
+    absstat_accum would (act_aware_utils.py:64-74) -- the statistic is a side output of the GEMM that consumes x."""
+    _require_cuda(x, weight, bias, acc)
+    lib = load()
+    m, n = weight.shape
+    x2 = x.reshape(-1, n)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    if acc.dtype != x.dtype or acc.numel() != n or not acc.is_contiguous():
+        raise ValueError("acc must be a contiguous [n] tensor of the activation dtype")
+    mode = STAT_ABS_MEAN if "abs_mean" in method else STAT_ABS_MAX
+    M = x2.shape[0]
+    y = torch.empty(M, m, dtype=x.dtype, device=x.device)
+    scratch = torch.empty(4 * n, dtype=torch.uint8, device=x.device)
+    if bias is not None and not bias.is_contiguous():
+        bias = bias.contiguous()
+    with torch.cuda.device(x.device):
+        _check(lib.asvd_linear_forward_stat(x2.data_ptr(), x2.stride(0), M, n, weight.data_ptr(), weight.stride(0), m,
+                                            None if bias is None else bias.data_ptr(), y.data_ptr(), m, dtype_code(x.dtype), mode,
+                                            acc.data_ptr(), scratch.data_ptr(), 4 * n, _stream()))
+    return y.reshape(*x.shape[:-1], m)
 
 
 def launch_count() -> int:

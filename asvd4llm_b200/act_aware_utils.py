@@ -35,27 +35,58 @@ def calib_input_distribution(model, calib_loader, method, use_cache=True):
         return
     model.eval()
 
-    def hook(module, inp, out):
-        x = inp[0].detach()
+    def check_batch1(x):
         if x.dim() > 2 and x.numel() // (x.shape[-1] * x.shape[-2]) != 1:
             # upstream's `.view(-1)` (:66) is only meaningful for batch 1
             raise ValueError("calib_input_distribution expects batch-1 activations, got " + str(tuple(x.shape)))
+
+    def accumulator(module, x):
         acc = module.scaling_diag_matrix
         if not torch.is_tensor(acc):                           # python int 0 until the first call (:80)
             acc = torch.zeros(x.shape[-1], dtype=x.dtype, device=x.device)
             module.scaling_diag_matrix = acc
+        return acc
+
+    def hook(module, inp, out):
+        x = inp[0].detach()
+        check_batch1(x)
+        acc = accumulator(module, x)
         if "abs_mean" in method or "abs_max" in method:
             _lib.absstat_accum(x, acc, method)
 
+    def fused_forward(module):
+        # the layer's own GEMM produces the statistic of its input as a side output
+        # (asvd_linear_forward_stat) -- no hook, no second pass over the activation
+        def forward(x):
+            if torch.is_grad_enabled() or not _lib.linear_stat_eligible(x, module.weight, module.bias):
+                y = nn.functional.linear(x, module.weight, module.bias)
+                hook(module, (x,), y)
+                return y
+            check_batch1(x)
+            return _lib.linear_forward_stat(x.detach(), module.weight.data, None if module.bias is None else module.bias.data,
+                                            accumulator(module, x), method)
+        return forward
+
+    # ASVD_B200_CALIB=hook keeps upstream's structure (model forward by torch, statistic in a forward hook)
+    fused = os.environ.get("ASVD_B200_CALIB", "fused") != "hook" and ("abs_mean" in method or "abs_max" in method)
     handles = []
+    patched = []
     for _, module in model.named_modules():
         if isinstance(module, nn.Linear):
             module.scaling_diag_matrix = 0
-            handles.append(module.register_forward_hook(hook))
+            if fused and type(module) is nn.Linear and module.weight.is_cuda and module.weight.dtype in (torch.float16, torch.bfloat16):
+                module.forward = fused_forward(module)
+                patched.append(module)
+            else:
+                handles.append(module.register_forward_hook(hook))
     device = getattr(model, "device", None) or next(model.parameters()).device
-    for batch in calib_loader:
-        batch = {k: v.to(device) for k, v in batch.items()}
-        model(**batch)
+    try:
+        for batch in calib_loader:
+            batch = {k: v.to(device) for k, v in batch.items()}
+            model(**batch)
+    finally:
+        for module in patched:
+            del module.forward                                  # back to nn.Linear.forward
     table = {}
     for name, module in model.named_modules():
         if isinstance(module, nn.Linear):

@@ -13,6 +13,10 @@ int gemm_tn_tc(const T* A, int64_t lda, const T* B, int64_t ldb, T* C, int64_t l
 template <typename T>
 int gemm_tn_tc2(const T* A, int64_t lda, const T* B, int64_t ldb, T* C, int64_t ldc, const T* bias, int M, int N, int K,
                 cudaStream_t st, int bn_force);
+// y = A B^T + bias as above, and |A| reduced over the rows into stat32[K] (fp32, pre-zeroed; sum, or maximum when stat_max)
+template <typename T>
+int gemm_tn_tc2_stat(const T* A, int64_t lda, const T* B, int64_t ldb, T* C, int64_t ldc, const T* bias, int M, int N, int K,
+                     float* stat32, int stat_max, cudaStream_t st);
 // fused forward for ranks <= 256 (gemm_fused.cu): y = ((x Bw^T) -> 16-bit) Aw^T + bias in one kernel
 template <typename T>
 int lowrank_fused(const T* x, int64_t ldx, int M, int n, const T* Bw, int64_t ldb, int r, const T* Aw, int64_t lda, int m,

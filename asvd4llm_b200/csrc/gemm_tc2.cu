@@ -51,10 +51,16 @@ template <> __device__ __forceinline__ uint32_t pack2_<__nv_bfloat16>(float a, f
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <typename T>
+// STAT (calibration, SURVEY 8f N3 / act_aware_utils.py:64-74): the kernel also reduces |A| over the rows -- per column of
+// the activation the sum (abs_mean) or the maximum (abs_max) -- into stat32[K] (fp32, pre-zeroed): the spare warp of every
+// CTA walks 128 x 64 blocks of A with plain coalesced loads while the tensor pipe works (the blocks are the ones the TMA
+// just pulled through L2: no second HBM pass), so the statistic is a side output of the GEMM that consumes the
+// activation instead of a separate pass over it.
+template <typename T, bool STAT>
 __global__ void __launch_bounds__(g2::THREADS, 1)
 gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmC, const T* __restrict__ bias, int M, int N, int K, int BN) {
+                const __grid_constant__ CUtensorMap tmC, const T* __restrict__ bias, int M, int N, int K, int BN,
+                const T* __restrict__ Araw, int64_t lda, float* __restrict__ stat32, int stat_max) {
   using namespace g2;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -138,6 +144,31 @@ gemm_tn2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     }
+  } else if (STAT && warp == 3) {
+    using T2 = typename std::conditional<std::is_same<T, __half>::value, __half2, __nv_bfloat162>::type;
+    const int kb = (K + 63) >> 6, mb = (M + 127) >> 7;
+    for (int item = blockIdx.x; item < mb * kb; item += gridDim.x) {
+      const int r0 = (item / kb) << 7, c = ((item % kb) << 6) + 2 * lane;       // K is even (16-byte rows): c + 1 < K
+      if (c >= K) continue;
+      const int r1 = min(M, r0 + 128);
+      float s0 = 0.f, s1 = 0.f;
+      unsigned m0u = 0u, m1u = 0u;                  // |x| >= 0: its bit pattern orders like the value, NaN above everything
+      const T* p = Araw + (int64_t)r0 * lda + c;
+#pragma unroll 4
+      for (int r = r0; r < r1; ++r, p += lda) {
+        const T2 v = *reinterpret_cast<const T2*>(p);
+        const float a = fabsf(to_f32<T>(v.x)), b = fabsf(to_f32<T>(v.y));
+        if (stat_max) { m0u = max(m0u, __float_as_uint(a)); m1u = max(m1u, __float_as_uint(b)); }
+        else { s0 += a; s1 += b; }
+      }
+      if (stat_max) {
+        atomicMax(reinterpret_cast<unsigned*>(stat32) + c, m0u);
+        atomicMax(reinterpret_cast<unsigned*>(stat32) + c + 1, m1u);
+      } else {
+        atomicAdd(stat32 + c, s0);
+        atomicAdd(stat32 + c + 1, s1);
+      }
+    }
   } else if (warp >= 4) {
     // epilogue: warp = (TMEM lane quadrant q, 128-column half h).  Accumulator -> registers -> + bias -> 16-bit ->
     // staging tile in shared memory (rows of 128 B, 16-byte chunks XOR row&7 = the 128-byte TMA swizzle) -> TMA store.
@@ -215,9 +246,10 @@ static int choose_bn(int M, int N, int nclusters_max) {
 }
 
 // returns 0 on launch, 1 if the operands do not meet TMA's alignment rules, <0 on error.  bn_force: 0 = choose.
-template <typename T>
-int gemm_tn_tc2(const T* A, int64_t lda, const T* B, int64_t ldb, T* C, int64_t ldc, const T* bias, int M, int N, int K,
-                cudaStream_t st, int bn_force) {
+// stat32 != nullptr: also reduce |A| over the rows into stat32[K] (sum, or maximum when stat_max), see the kernel.
+template <typename T, bool STAT>
+static int gemm_tn_tc2_impl(const T* A, int64_t lda, const T* B, int64_t ldb, T* C, int64_t ldc, const T* bias, int M, int N, int K,
+                            cudaStream_t st, int bn_force, float* stat32, int stat_max) {
   using namespace g2;
   auto ok = [](const void* p, int64_t ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld * 2) % 16 == 0; };
   if (!ok(A, lda) || !ok(B, ldb) || !ok(C, ldc) || K < 1) return 1;
@@ -230,7 +262,7 @@ int gemm_tn_tc2(const T* A, int64_t lda, const T* B, int64_t ldb, T* C, int64_t 
     cudaDeviceGetAttribute(&sms_dev[slot], cudaDevAttrMultiProcessorCount, dev);
   }
   if (!attr[slot]) {
-    if (cudaFuncSetAttribute(gemm_tn2_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess) return -2;
+    if (cudaFuncSetAttribute(gemm_tn2_kernel<T, STAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess) return -2;
     attr[slot] = true;
   }
   const int ncl_max = sms_dev[slot] / 2;
@@ -254,10 +286,25 @@ int gemm_tn_tc2(const T* A, int64_t lda, const T* B, int64_t ldb, T* C, int64_t 
   lattr[0].val.clusterDim.x = 2; lattr[0].val.clusterDim.y = 1; lattr[0].val.clusterDim.z = 1;
   cfg.attrs = lattr;
   cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, gemm_tn2_kernel<T>, tmA, tmB, tmC, bias, M, N, K, BN) != cudaSuccess) return -2;
+  if (cudaLaunchKernelEx(&cfg, gemm_tn2_kernel<T, STAT>, tmA, tmB, tmC, bias, M, N, K, BN, A, lda, stat32, stat_max) != cudaSuccess) return -2;
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
+template <typename T>
+int gemm_tn_tc2(const T* A, int64_t lda, const T* B, int64_t ldb, T* C, int64_t ldc, const T* bias, int M, int N, int K,
+                cudaStream_t st, int bn_force) {
+  return gemm_tn_tc2_impl<T, false>(A, lda, B, ldb, C, ldc, bias, M, N, K, st, bn_force, nullptr, 0);
+}
+template <typename T>
+int gemm_tn_tc2_stat(const T* A, int64_t lda, const T* B, int64_t ldb, T* C, int64_t ldc, const T* bias, int M, int N, int K,
+                     float* stat32, int stat_max, cudaStream_t st) {
+  return gemm_tn_tc2_impl<T, true>(A, lda, B, ldb, C, ldc, bias, M, N, K, st, 0, stat32, stat_max);
+}
+
+template int gemm_tn_tc2_stat<__half>(const __half*, int64_t, const __half*, int64_t, __half*, int64_t, const __half*, int, int, int,
+                                      float*, int, cudaStream_t);
+template int gemm_tn_tc2_stat<__nv_bfloat16>(const __nv_bfloat16*, int64_t, const __nv_bfloat16*, int64_t, __nv_bfloat16*, int64_t,
+                                             const __nv_bfloat16*, int, int, int, float*, int, cudaStream_t);
 template int gemm_tn_tc2<__half>(const __half*, int64_t, const __half*, int64_t, __half*, int64_t, const __half*, int, int, int,
                                  cudaStream_t, int);
 template int gemm_tn_tc2<__nv_bfloat16>(const __nv_bfloat16*, int64_t, const __nv_bfloat16*, int64_t, __nv_bfloat16*, int64_t,

@@ -115,6 +115,22 @@ __global__ void absstat_combine_kernel(const float* __restrict__ partial, int n,
   }
 }
 
+// fused calibration (asvd_linear_forward_stat): fp32 column sums / maxima of |x| from the GEMM kernel -> the hook's update
+template <typename T>
+__global__ void stat_finalize_kernel(const float* __restrict__ stat32, int n, int64_t L, int mode, T* __restrict__ acc) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const float v = stat32[j];
+  const float old = to_f32<T>(acc[j]);
+  if (mode != ASVD_STAT_ABS_MAX) {
+    const float mean = to_f32<T>(from_f32<T>(v / (float)L));
+    acc[j] = from_f32<T>(old + mean);
+  } else {
+    const float cur = to_f32<T>(from_f32<T>(v));
+    acc[j] = from_f32<T>(cur > old ? cur : old);           // torch.where(abs_max > acc, abs_max, acc): a NaN maximum is dropped
+  }
+}
+
 }  // namespace asvd
 
 using namespace asvd;
@@ -249,6 +265,37 @@ int asvd_absstat_accum(const void* x, int64_t ldx, int64_t L, int n, int dtype, 
   }
   set_error("bad dtype %d", dtype);
   return ASVD_ERR_INVALID;
+}
+
+int asvd_linear_forward_stat(const void* x, int64_t ldx, int64_t M, int n, const void* W, int64_t ldw, int m, const void* bias,
+                             void* y, int64_t ldy, int dtype, int mode, void* acc, void* scratch, size_t scratch_bytes,
+                             void* stream) {
+  ASVD_REQUIRE(x && W && y && acc && scratch, "null pointer");
+  ASVD_REQUIRE(M > 0 && M < (1ll << 31) && n > 0 && m > 0 && ldx >= n && ldw >= n && ldy >= m, "bad shape");
+  ASVD_REQUIRE(mode == ASVD_STAT_ABS_MEAN || mode == ASVD_STAT_ABS_MAX, "bad mode %d", mode);
+  ASVD_REQUIRE(dtype == ASVD_F16 || dtype == ASVD_BF16, "16-bit activations only (fp32 modules keep the hook path)");
+  if (scratch_bytes < sizeof(float) * (size_t)n) { set_error("scratch too small"); return ASVD_ERR_WORKSPACE; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* stat32 = reinterpret_cast<float*>(scratch);
+  ASVD_CUDA_CHECK(cudaMemsetAsync(stat32, 0, sizeof(float) * (size_t)n, st));
+  prof_begin(K_FORWARD, st);
+  int rc;
+  if (dtype == ASVD_F16)
+    rc = tc::gemm_tn_tc2_stat<__half>((const __half*)x, ldx, (const __half*)W, ldw, (__half*)y, ldy, (const __half*)bias, (int)M, m, n,
+                                      stat32, mode == ASVD_STAT_ABS_MAX, st);
+  else
+    rc = tc::gemm_tn_tc2_stat<__nv_bfloat16>((const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)W, ldw, (__nv_bfloat16*)y, ldy,
+                                             (const __nv_bfloat16*)bias, (int)M, m, n, stat32, mode == ASVD_STAT_ABS_MAX, st);
+  prof_end(K_FORWARD, st);
+  if (rc == 1) { set_error("operands are not 16-byte aligned row-wise (in/out features must be multiples of 8)"); return ASVD_ERR_INVALID; }
+  if (rc != 0) { set_error("GEMM launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return ASVD_ERR_CUDA; }
+  dim3 grid((n + 255) / 256);
+  if (dtype == ASVD_F16)
+    ASVD_LAUNCH(K_STAT, st, (stat_finalize_kernel<__half><<<grid, 256, 0, st>>>(stat32, n, M, mode, (__half*)acc)));
+  else
+    ASVD_LAUNCH(K_STAT, st, (stat_finalize_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(stat32, n, M, mode, (__nv_bfloat16*)acc)));
+  ASVD_CUDA_CHECK(cudaGetLastError());
+  return ASVD_OK;
 }
 
 size_t asvd_lowrank_forward_scratch_bytes(int64_t M, int r, int m) {

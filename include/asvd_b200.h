@@ -124,6 +124,18 @@ size_t asvd_absstat_scratch_bytes(int n);
 int asvd_absstat_accum(const void* x, int64_t ldx, int64_t L, int n, int dtype, int mode, void* acc,
                        void* scratch, size_t scratch_bytes, void* stream);
 
+/* ---- a1 fused into its producer: one calibration step of one nn.Linear -- the layer's own forward
+ * y = x W^T + bias AND the hook's statistic of its input x (act_aware_utils.py:64-74) in the same tcgen05 GEMM kernel: a
+ * spare warp of every CTA reduces |x| over the rows while the tensor pipe works, so the activation is not read a second
+ * time from HBM and the hook's separate launches disappear.
+ *   x [M, n] ldx;  W [m, n] ldw (nn.Linear.weight);  bias [m] or NULL;  y [M, m] ldy;  F16 / BF16 only, rows 16-byte aligned
+ *   mode ABS_MEAN / ABS_MAX;  acc [n] in the activation dtype, updated exactly as asvd_absstat_accum does (the fp32 column
+ *   sums are combined with atomics, so the last bit of an ABS_MEAN update is not run-to-run deterministic)
+ *   scratch: 4 n bytes. */
+int asvd_linear_forward_stat(const void* x, int64_t ldx, int64_t M, int n, const void* W, int64_t ldw, int m,
+                             const void* bias, void* y, int64_t ldy, int dtype, int mode, void* acc, void* scratch,
+                             size_t scratch_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

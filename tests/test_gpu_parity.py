@@ -912,3 +912,59 @@ def test_mixed_convergence_batch_is_bitwise_independent():
         A1, B1 = single.extract(400, "UV", torch.float16, 0)
         A2, B2 = fact.extract(400, "UV", torch.float16, b)
         assert torch.equal(A1, A2) and torch.equal(B1, B2), b
+
+
+# ------------------------------------------------------------------------------------------------ N3: statistic fused into its producer
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("method", ["abs_mean", "abs_max"])
+def test_linear_forward_stat_matches_linear_and_hook_math(dtype, method):
+    """asvd_linear_forward_stat: the layer output equals the library linear to output rounding, and the accumulator gets
+    the hook's update (act_aware_utils.py:64-74, oracle abs_stat_update) -- over two calls, ragged M, with and without bias."""
+    L = _lib()
+    g = torch.Generator().manual_seed(17)
+    for (M, n, m, with_bias) in [(2048, 768, 3072, True), (333, 64, 136, False), (1, 8, 8, True), (700, 1024, 6280, True)]:
+        W = (torch.randn(m, n, generator=g) / n ** 0.5).to(dtype)
+        bias = (torch.randn(m, generator=g) * 0.1).to(dtype) if with_bias else None
+        acc = torch.zeros(n, dtype=dtype, device="cuda")
+        ref_acc = 0
+        for call in range(2):
+            x = (torch.randn(1, M, n, generator=g) * (1.0 + call)).to(dtype)
+            assert L.linear_stat_eligible(x.cuda(), W.cuda(), None if bias is None else bias.cuda())
+            y = L.linear_forward_stat(x.cuda(), W.cuda(), None if bias is None else bias.cuda(), acc, method)
+            yref = torch.nn.functional.linear(x.cuda(), W.cuda(), None if bias is None else bias.cuda())
+            tol = (2e-2 if dtype == torch.bfloat16 else 3e-3) * max(1.0, yref.float().abs().max().item())
+            assert y.shape == yref.shape and (y.float() - yref.float()).abs().max().item() < tol
+            ref_acc = O.abs_stat_update(ref_acc, x, method)
+        rtol = 2e-2 if dtype == torch.bfloat16 else 2e-3                 # one ulp of the accumulator dtype
+        assert torch.allclose(acc.float().cpu(), ref_acc.float(), rtol=rtol, atol=1e-6), (M, n, m, method)
+    # NaN: the mean propagates it (`+= abs_mean`), upstream's `torch.where(abs_max > acc, abs_max, acc)` drops it
+    x = torch.ones(1, 16, 8, dtype=dtype); x[0, 3, 2] = float("nan")
+    acc = torch.zeros(8, dtype=dtype, device="cuda")
+    L.linear_forward_stat(x.cuda(), torch.eye(8, dtype=dtype).cuda(), None, acc, method)
+    ref = O.abs_stat_update(torch.zeros(8, dtype=dtype), x, method)
+    assert torch.equal(torch.isnan(acc.cpu()), torch.isnan(ref)) and torch.isfinite(acc[[0, 1, 3, 4, 5, 6, 7]]).all()
+
+
+def test_fused_calibration_matches_hook_path(golden_pipeline, tmp_path, monkeypatch):
+    """calib_input_distribution on a 16-bit model: the fused path (statistic as a side output of every layer's GEMM) against
+    upstream's structure (torch forward + hook, ASVD_B200_CALIB=hook).  The two forwards differ by GEMM rounding, so the
+    statistics agree to a few ulps of fp16, not bitwise."""
+    from asvd4llm_b200.act_aware_utils import calib_input_distribution
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("cache")
+    loader = golden_pipeline["loader"]
+    out = {}
+    for mode in ("hook", "fused"):
+        monkeypatch.setenv("ASVD_B200_CALIB", mode)
+        for method in ("abs_mean", "abs_max"):
+            model = build_tiny_opt(golden_pipeline).half().cuda()
+            before = _lib().profile_read()["forward"][1]
+            calib_input_distribution(model, loader, method, use_cache=False)
+            used_gemm = _lib().profile_read()["forward"][1] > before
+            assert used_gemm == (mode == "fused")
+            assert all("forward" not in vars(mod) for mod in model.modules())       # patched forwards are gone again
+            out[(mode, method)] = {n: mod.scaling_diag_matrix.float().cpu() for n, mod in model.named_modules() if isinstance(mod, nn.Linear)}
+    for method in ("abs_mean", "abs_max"):
+        for name, ref in out[("hook", method)].items():
+            got = out[("fused", method)][name]
+            assert torch.allclose(got, ref, rtol=1e-2, atol=1e-4), (method, name, (got - ref).abs().max().item())
