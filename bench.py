@@ -122,10 +122,33 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------- CPU arm
+_UPSTREAM = "unset"
+
+
+def upstream_module():
+    """upstream's own modules/svd_linear.py staged in oracle/_ref (oracle/make_ref.py), or None."""
+    global _UPSTREAM
+    if _UPSTREAM == "unset":
+        try:
+            from oracle import make_ref
+            _UPSTREAM = make_ref.load_upstream_svd_linear()
+        except Exception:      # noqa
+            _UPSTREAM = None
+    return _UPSTREAM
+
+
+def reference_kind():
+    return "reference" if upstream_module() is not None else "port"
+
+
 def reference_step(lin, O, method="lowrank"):
     """One unit of the reference's CPU path (modules/svd_linear.py:26-103: scale, SVD, un-scale, fuse, cast).
-    method="lowrank" is what upstream ships (torch.svd_lowrank, q = rank, niter 2); "exact" is torch.linalg.svd, the
-    oracle north_star names."""
+    method="lowrank" is what upstream ships (torch.svd_lowrank, q = rank, niter 2): upstream's OWN file when oracle/_ref
+    holds it (kind "reference"), else the oracle's restatement (kind "port"); "exact" is torch.linalg.svd, the oracle
+    north_star names (restatement only: upstream has no such code path)."""
+    up = upstream_module()
+    if method == "lowrank" and up is not None:
+        return up.SVDLinear.from_linear(lin, RATIO, act_aware=True, alpha=ALPHA, sigma_fuse="UV")
     return O.from_linear(lin, RATIO, act_aware=True, alpha=ALPHA, sigma_fuse="UV", method=method)
 
 
@@ -192,7 +215,7 @@ def run_reference(args, rank, world):
         _emit({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": 1,
                "warmup": 0, "ms_per_step": total * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic", "config": {"workload": LLAMA_WORKLOAD},
-               "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+               "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": reference_kind(),
                                 "sample": "one weight of each of the four shapes timed (svd_lowrank q=rank niter=2), multiplied by the shape's count: "
                                           + json.dumps(per_shape)},
                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
@@ -211,8 +234,10 @@ def run_reference(args, rank, world):
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": svd_config(_default_batch_static(), 1843),
-        "run": {"where": "host CPU, oracle port of the upstream algorithm; one weight per CPU step (a bounded sample of the GPU arm's batch)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "run": {"where": ("host CPU, upstream's own modules/svd_linear.py (oracle/_ref)" if reference_kind() == "reference"
+                          else "host CPU, oracle port of the upstream algorithm")
+                         + "; one weight per CPU step (a bounded sample of the GPU arm's batch)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": reference_kind(), "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -229,7 +254,7 @@ def llama_cpu_estimate(O):
     for (m, n), c in counts.items():
         lin = make_cpu_linear(7, m, n)
         t0 = time.perf_counter()
-        O.from_linear(lin, RATIO, act_aware=True, alpha=ALPHA, sigma_fuse="UV", method="lowrank")
+        reference_step(lin, O)
         dt = time.perf_counter() - t0
         per_shape[f"{m}x{n}"] = {"count": c, "s_per_matrix": round(dt, 3)}
         total += c * dt
@@ -516,7 +541,7 @@ def svd_baselines(dev, pool):
                                   + " on this GPU (cuSOLVER / cuBLAS), SVD only, one weight"}
         except Exception as e:      # noqa
             legs[name] = {"error": str(e)[:200]}
-    return {"value": 1.0 / t_low, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+    return {"value": 1.0 / t_low, "unit": UNIT, "cores": torch.get_num_threads(), "kind": reference_kind(),
             "sample": "one 4096x4096 fp16 weight @0.9: 3 x upstream's svd_lowrank path (median) and 1 x torch.linalg.svd on the host cores; "
                       "same weight through torch on this GPU for context", "legs": legs}
 
@@ -712,7 +737,7 @@ def main():
                 from oracle import asvd_oracle as O
                 torch.set_num_threads(_host_threads())
                 per_shape, total = llama_cpu_estimate(O)
-                cpu = {"value": 225 / total, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                cpu = {"value": 225 / total, "unit": UNIT, "cores": torch.get_num_threads(), "kind": reference_kind(),
                        "sample": "one weight of each of the four shapes timed on the host (upstream's svd_lowrank path), multiplied by the shape's count: "
                                  + json.dumps(per_shape)}
             _emit({"metric": METRIC, "value": res["matrices_per_s"], "unit": UNIT, "n_gpus": ctx.world, "steps": 1, "warmup": 0,

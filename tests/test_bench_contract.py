@@ -18,7 +18,8 @@ def test_reference_arm_prints_one_json_line_with_all_host_threads():
     assert d["steps"] == 1 and d["warmup"] == 1 and d["value"] > 0 and d["vs_baseline"] is None
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["value"] == d["value"] and "4096x4096" in cb["sample"]
+    staged = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "modules", "svd_linear.py"))
+    assert cb["kind"] == ("reference" if staged else "port") and cb["value"] == d["value"] and "4096x4096" in cb["sample"]
     assert cb["cores"] == len(os.sched_getaffinity(0))     # not the single thread OMP_NUM_THREADS=1 asks for
     assert "workload" in d["config"] and "model" not in d["config"]
     # the GPU arm prints the same `config` dict (bench.svd_config); run-dependent details live under `run`
