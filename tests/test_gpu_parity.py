@@ -152,6 +152,27 @@ def test_edge_cases():
     lin.weight.data[3, 5] = float("nan")
     out = SVDLinear.from_linear(lin, 0.9)
     assert isinstance(out, nn.Linear) and out.weight.shape == lin.weight.shape and out.weight.dtype == torch.float16
+    # ... and PER LAYER, as upstream's loop would: the healthy layers of the same kernel batch are decomposed normally,
+    # bitwise as if the bad layer had not been there (an Inf in the statistics counts as a bad layer too)
+    from asvd4llm_b200.modules.svd_linear import from_linear_batch
+    gb = torch.Generator().manual_seed(8)
+    lins = []
+    for i in range(4):
+        l = nn.Linear(96, 80, bias=False)
+        l.weight.data = (torch.randn(80, 96, generator=gb) * 0.05).half()
+        l = l.cuda()
+        l.scaling_diag_matrix = (torch.rand(96, generator=gb) + 0.1).half().cuda()
+        lins.append(l)
+    lins[1].weight.data[7, 7] = float("nan")
+    lins[3].scaling_diag_matrix[5] = float("inf")
+    with contextlib.redirect_stdout(io.StringIO()) as buf:
+        mods = from_linear_batch(lins, [0.8] * 4, act_aware=True, alpha=0.5)
+    assert buf.getvalue().count("nan in S") == 2
+    assert [isinstance(m, SVDLinear) for m in mods] == [True, False, True, False]
+    for i in (0, 2):
+        alone = SVDLinear.from_linear(lins[i], 0.8, act_aware=True, alpha=0.5)
+        assert torch.equal(alone.ALinear.weight.data, mods[i].ALinear.weight.data)
+        assert torch.equal(alone.BLinear.weight.data, mods[i].BLinear.weight.data)
     # act_aware without statistics raises like upstream
     lin2 = nn.Linear(64, 48).cuda()
     with pytest.raises(AttributeError):
