@@ -62,6 +62,8 @@ class ClockSampler:
         self.result = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
 
     def start(self):
+        if os.environ.get("ASVD_BENCH_NO_SAMPLER") == "1":     # experiments only: is the sampler itself perturbing the run?
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -337,8 +339,14 @@ def svd_workload(ctx):
         return fact, outs
 
     clocks = ClockSampler(ctx.local).start()             # NVML start-up happens during the warm-up, not the timed region
+    # Every step drops the previous step's factorisation before it allocates its own workspace (4.6 GB at 18 weights), as a
+    # pipeline that consumes the factors would: with two workspaces alive in turn the caching allocator sooner or later
+    # splits the free one for the 15 MB factor tensors and has to cudaMalloc a fresh 4.6 GB block mid-run -- the "hiccup"
+    # that kept landing on the second timed step (843 -> 900-1270 ms; profiles/r02_bench_hiccup.log).
+    fact = outs = None
     for i in range(args.warmup):
-        fact, _ = device_step(i)
+        fact = outs = None
+        fact, outs = device_step(i)
     ctx.barrier()
     # A freshly booted box has been seen to take one step 40-80 % longer than its neighbours about a second into the load
     # (sw_power_cap flagged, clocks back at maximum right after): keep warming up, untimed, until two consecutive steps
@@ -347,7 +355,8 @@ def svd_workload(ctx):
     extra, prev, t_load = 0, None, time.perf_counter()
     while extra < 12:
         t0 = time.perf_counter()
-        device_step(extra)
+        fact = outs = None
+        fact, outs = device_step(extra)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         extra += 1
@@ -365,6 +374,7 @@ def svd_workload(ctx):
     e0.record()
     marks[0].record()
     for i in range(args.steps):
+        fact = outs = None
         fact, outs = device_step(i)
         marks[i + 1].record()
     e1.record()
