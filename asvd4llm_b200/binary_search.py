@@ -7,11 +7,10 @@ import time
 from collections import defaultdict
 
 import torch
-import torch.nn as nn
 
 from . import _lib
 from .evaluate_utils import evaluate_perplexity
-from .modules.svd_linear import SVDLinear, from_linear_batch, clear_cache
+from .modules.svd_linear import from_linear_batch, clear_cache
 from .sensitivity import enumerate_linears
 
 

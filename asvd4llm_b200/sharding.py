@@ -9,7 +9,7 @@ results once per phase.
 """
 from __future__ import annotations
 
-from typing import Dict, Iterable, List, Sequence, Optional
+from typing import Dict, Iterable, List
 
 import torch
 import torch.distributed as dist
