@@ -21,6 +21,7 @@
 #include "umma.cuh"
 #include "gemm_tc.h"
 #include <type_traits>
+#include <stdlib.h>
 
 namespace asvd {
 namespace tc {
@@ -274,7 +275,11 @@ static int gemm_tn_tc2_impl(const T* A, int64_t lda, const T* B, int64_t ldb, T*
   if (!make_tmap_2d(&tmB, dt, 2, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)BN / 2, BK)) return -1;
   if (!make_tmap_2d(&tmC, dt, 2, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, BM, 64)) return -1;
   const int64_t tiles = (int64_t)((M + 255) / 256) * ((N + BN - 1) / BN);
-  const int nclusters = (int)(tiles < ncl_max ? tiles : ncl_max);
+  int nclusters = (int)(tiles < ncl_max ? tiles : ncl_max);
+  if (const char* mc = getenv("ASVD_B200_FWD_MAXCL")) {        // experiments: leave SMs to a kernel on another stream
+    const int lim = atoi(mc);
+    if (lim > 0 && lim < nclusters) nclusters = lim;
+  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * nclusters);
