@@ -74,7 +74,10 @@ def calib_input_distribution(model, calib_loader, method, use_cache=True):
     for _, module in model.named_modules():
         if isinstance(module, nn.Linear):
             module.scaling_diag_matrix = 0
-            if fused and type(module) is nn.Linear and module.weight.is_cuda and module.weight.dtype in (torch.float16, torch.bfloat16):
+            # (a module whose `forward` is already an instance attribute -- accelerate's device_map hooks wrap it that way --
+            # keeps its wrapper and gets the plain hook)
+            if (fused and type(module) is nn.Linear and "forward" not in vars(module) and module.weight.is_cuda
+                    and module.weight.dtype in (torch.float16, torch.bfloat16)):
                 module.forward = fused_forward(module)
                 patched.append(module)
             else:
