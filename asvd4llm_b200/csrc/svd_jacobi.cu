@@ -1712,6 +1712,11 @@ static int do_extract(const SvdPlan& p, const unsigned char* ws, int b, int r, i
 extern "C" {
 
 int asvd_version(void) { return ASVD_B200_VERSION; }
+#ifdef ASVD_SOLVE_TIMING
+int asvd_debug_solve_timing(unsigned long long* out8) {       // timing builds only (scripts/solve_timing.py)
+  return cudaMemcpyFromSymbol(out8, asvd::g_solve_timing, 8 * sizeof(unsigned long long)) == cudaSuccess ? 0 : 1;
+}
+#endif
 const char* asvd_last_error(void) { return asvd::last_error(); }
 
 void asvd_profile_enable(int on) { asvd::prof_reset(on != 0); }

@@ -87,8 +87,17 @@ __device__ __forceinline__ void quad_cols(float (&g)[8][8], const float2 (&q)[4]
   }
 }
 
-__device__ __forceinline__ void load_q4(const float2* src, float2 (&q)[4]) {
-  const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 2);
+// A step's 64 rotations (16 groups x 4 pivots x float2) are stored as TWO PLANES of 16 float4: plane 0 holds pivots 0-1
+// of every group, plane 1 pivots 2-3, so that the 16 lanes of a half-warp (group = lane & 15) read 256 consecutive bytes
+// per LDS.128.  With the four pivots of a group side by side (32-byte stride) every such load was a 2-way bank conflict,
+// a third of the kernel's shared-memory wavefronts -- and the lead warp's dependent chain queues behind exactly that
+// traffic (its own loads and shuffles share the pipe: profiles/r02_solve_timing.log).
+__device__ __forceinline__ float4* q_plane(float2* step_base, int grp, int plane) {
+  return reinterpret_cast<float4*>(step_base) + plane * 16 + grp;
+}
+__device__ __forceinline__ void load_q4(const float2* step_base, int grp, float2 (&q)[4]) {
+  const float4* p4 = reinterpret_cast<const float4*>(step_base);
+  const float4 a = p4[grp], b = p4[16 + grp];
   q[0] = make_float2(a.x, a.y); q[1] = make_float2(a.z, a.w); q[2] = make_float2(b.x, b.y); q[3] = make_float2(b.z, b.w);
 }
 
@@ -96,69 +105,66 @@ __device__ __forceinline__ void load_q4(const float2* src, float2 (&q)[4]) {
 // computes the four rotations of every group from its registers, publishes them and only ARRIVES at the step's named
 // barrier, so it runs ahead of the other seven warps (which wait on that barrier) by up to a whole round; the barrier
 // ids of a round are distinct and the blocking barriers of the quad move separate their reuse.
+#ifdef ASVD_SOLVE_TIMING
+__device__ unsigned long long g_solve_timing[16];
+#define QT_MARK(k) do { if (gtid == 0) { const long long _t = clock64(); qt_acc[k] += _t - qt_last; qt_last = _t; } } while (0)
+__shared__ long long qt_acc[12];
+__shared__ long long qt_last;
+#else
+#define QT_MARK(k) do { } while (0)
+#endif
+
 template <int TYPE, bool LEAN = false>
 __device__ __forceinline__ void quad_g_step(float (&g)[8][8], float (&d)[8], bool lead, bool is_diag, float2* cs_step, int pa,
                                             int pc, int gtid, uint64_t* mb, int step, int bar_id,
                                             float2* __restrict__ hist_step = nullptr) {
   if (lead) {
-    // The parameter arithmetic is the dependent chain of the whole sweep (~35 instructions per pivot at ~4 cycles
-    // each for a single warp), so it is spread over all 32 lanes: diagonal lane L keeps pivots 0 and 1 and hands
-    // pivots 2 and 3 to lane L + 16 (whose own patch needs no parameters), 10 shuffles out and 6 back.
-    const int lane = gtid & 31;
-    const bool upper = lane >= 16;
-    float in[2][5];
+    // The parameter arithmetic is the dependent chain of the whole sweep.  Every diagonal lane computes the four
+    // rotations of its group from its own registers (four independent chains of ~35 instructions interleave).  The first
+    // version handed pivots 2 and 3 to lane L + 16 -- 10 shuffles out, 6 back -- to halve the arithmetic per lane; measured
+    // (profiles/r02_solve_timing.log) those shuffles cost more than the whole arithmetic: they queue in the same
+    // shared-memory / shuffle pipe the other fifteen warps keep busy with their rotation loads.
+    QT_MARK(0);                                   // time since the end of the previous step's apply (moves, folds, ...)
+    float3 o[4];
 #pragma unroll
-    for (int kk = 0; kk < 2; ++kk) {
-      const int pl = qp_p(TYPE, kk), rl = qp_q(TYPE, kk), ph = qp_p(TYPE, kk + 2), rh = qp_q(TYPE, kk + 2);
-      const float mine[5] = {g[pl][pl], g[rl][rl], g[pl][rl], d[pl], d[rl]};
-      const float send[5] = {g[ph][ph], g[rh][rh], g[ph][rh], d[ph], d[rh]};
-#pragma unroll
-      for (int v = 0; v < 5; ++v) {
-        const float got = __shfl_sync(0xffffffffu, send[v], lane & 15);
-        in[kk][v] = upper ? got : mine[v];
-      }
+    for (int k = 0; k < 4; ++k) {
+      const int pl = qp_p(TYPE, k), rl = qp_q(TYPE, k);
+      o[k] = quad_rotation(g[pl][pl], g[rl][rl], g[pl][rl], d[pl], d[rl]);
     }
-    float3 o[2];
-#pragma unroll
-    for (int kk = 0; kk < 2; ++kk) o[kk] = quad_rotation(in[kk][0], in[kk][1], in[kk][2], in[kk][3], in[kk][4]);
-    float3 back[2];
-#pragma unroll
-    for (int kk = 0; kk < 2; ++kk) {
-      back[kk].x = __shfl_sync(0xffffffffu, o[kk].x, (lane & 15) + 16);
-      back[kk].y = __shfl_sync(0xffffffffu, o[kk].y, (lane & 15) + 16);
-      back[kk].z = __shfl_sync(0xffffffffu, o[kk].z, (lane & 15) + 16);
-    }
+    QT_MARK(2);                                   // rotation parameters
     if (is_diag) {
 #pragma unroll
-      for (int kk = 0; kk < 2; ++kk) {
-        d[qp_p(TYPE, kk)] *= o[kk].z; d[qp_q(TYPE, kk)] *= o[kk].z;
-        d[qp_p(TYPE, kk + 2)] *= back[kk].z; d[qp_q(TYPE, kk + 2)] *= back[kk].z;
-      }
-      *reinterpret_cast<float4*>(cs_step + 4 * pa) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
-      *reinterpret_cast<float4*>(cs_step + 4 * pa + 2) = make_float4(back[0].x, back[0].y, back[1].x, back[1].y);
+      for (int k = 0; k < 4; ++k) { d[qp_p(TYPE, k)] *= o[k].z; d[qp_q(TYPE, k)] *= o[k].z; }
+      *q_plane(cs_step, pa, 0) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+      *q_plane(cs_step, pa, 1) = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
       if (LEAN) {                                          // the replay kernel reads the rotations from HBM / L2
-        *reinterpret_cast<float4*>(hist_step + 4 * pa) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
-        *reinterpret_cast<float4*>(hist_step + 4 * pa + 2) = make_float4(back[0].x, back[0].y, back[1].x, back[1].y);
+        *q_plane(hist_step, pa, 0) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+        *q_plane(hist_step, pa, 1) = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
       }
     }
     __syncwarp();
     asm volatile("bar.arrive %0, 256;" ::"r"(bar_id) : "memory");
     if (!LEAN && gtid == 0) tc::mbar_arrive(&mb[step]);    // release: the R threads may consume this step
+    QT_MARK(3);                                   // shuffles back, publish, arrive
   } else {
     asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
   }
   float2 qr[4], qc[4];
-  load_q4(cs_step + 4 * pa, qr);
-  load_q4(cs_step + 4 * pc, qc);
+  load_q4(cs_step, pa, qr);
+  load_q4(cs_step, pc, qc);
+  if (lead) QT_MARK(4);                           // parameter loads
   quad_rows<TYPE>(g, qr);
   quad_cols<TYPE>(g, qc);
+#ifdef ASVD_SOLVE_TIMING
+  if (lead) { asm volatile("" ::"f"(g[0][0]), "f"(g[7][7]), "f"(g[3][4]) : "memory"); QT_MARK(5); }   // the lead warp's own 128 FMAs
+#endif
 }
 
 template <int TYPE, bool WAIT = true>
 __device__ __forceinline__ void quad_r_step(float (&r)[8][8], const float2* cs_step, int pc, uint64_t* mb, int step) {
   if (WAIT) tc::mbar_wait(&mb[step], 0);                   // acquire; every barrier of the array is used once
   float2 qc[4];
-  load_q4(cs_step + 4 * pc, qc);
+  load_q4(cs_step, pc, qc);
   quad_cols<TYPE>(r, qc);
 }
 
@@ -321,6 +327,10 @@ solve_quad_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat
     const bool lead = lt < 32;
     auto bar_g = [] { asm volatile("bar.sync 2, 256;" ::: "memory"); };
     bar_g();                                                 // every patch is in registers: G becomes the staging area
+#ifdef ASVD_SOLVE_TIMING
+    if (lt == 0) { for (int i = 0; i < 12; ++i) qt_acc[i] = 0; qt_last = clock64(); }
+    const int gtid = lt;
+#endif
 
     quad_g_step<0>(g, d, lead, is_diag, csh + 0 * 64, pa, pc, lt, mb, 0, 8);
     quad_g_step<1>(g, d, lead, is_diag, csh + 1 * 64, pa, pc, lt, mb, 1, 9);
@@ -349,6 +359,7 @@ solve_quad_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat
 #pragma unroll
           for (int j = 0; j < 8; ++j) g[i][j] *= dr[i] * dc[j];
       }
+      QT_MARK(6);                                  // (lead lane) fold, if any
       // ---- quad move: one pass through shared memory (rows and columns at once), only what changes place
       const unsigned char* qs = qsrc + r * 32;
       const int rsrcL = qs[2 * pa], rsrcH = qs[2 * pa + 1], csrcL = qs[2 * pc], csrcH = qs[2 * pc + 1];
@@ -366,7 +377,12 @@ solve_quad_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat
         for (int i = 0; i < 8; ++i) d[i] = dmov[(i < 4 ? rsrcL : rsrcH) + (i & 3)];
       }
       bar_g();               // blocking for the lead warp too: nobody writes the staging area while it is being read
+      QT_MARK(7);                                  // quad move incl. waiting for the other warps at its barriers
     }
+#ifdef ASVD_SOLVE_TIMING
+    if (lt == 0 && blockIdx.x == 0 && blockIdx.y == 0)
+      for (int i = 0; i < 8; ++i) g_solve_timing[i] = (unsigned long long)qt_acc[i];
+#endif
     // final diagonal (true norms) and scales, ranks for the norm sort
     if (is_diag) {
 #pragma unroll
