@@ -154,22 +154,26 @@ class Factorisation:
         return A, B
 
 
+SOLVE_CTAS_PER_SM = 3          # solve_tri_g_kernel: 160 threads x 128 registers, 74 KB of shared memory
+
+
 def suggest_batch(m: int, n: int, device=None, limit_bytes: int = 32 << 30) -> int:
     """How many same-shape weights to factorise per call.  Every kernel of a Jacobi round works one block pair (128
-    vectors) per CTA, and the inner eigen-solve -- 127 dependent rotation steps, one CTA per SM -- takes the same time for
-    one CTA as for a full wave of them, so batches are sized in whole WAVES of block pairs on the device's SMs.  Measured
-    (profiles/r02_ab_batch.jsonl, ms per matrix at 1 / 2 / 4 waves): 4096^2 57.3 / 49.9 / 47.4, 11008x4096 68.9 / 59.0 /
-    56.5, 4096x11008 84.0 / 72.5 / 69.9 -- the second wave fills the SMs the first leaves idle (4 x 32 pairs = 128 of 148)
-    and every further wave amortises the per-sweep host synchronisation.  Default: four waves (ASVD_B200_WAVES
-    overrides), at most 32 weights, bounded by the workspace budget."""
+    vectors) per CTA.  The inner eigen-solve (solve_tri_g_kernel) is a chain of 127 dependent rotation steps per pair that
+    takes about as long for one CTA as for a full SM, and THREE of its CTAs share an SM, so batches are sized in whole
+    solve waves of 3 x SMs block pairs: two of them by default (27 weights at 4096^2 on 148 SMs = 864 of 888 slots, 2.92
+    of 3 waves of the two-CTA replay kernel, 5.84 of 6 waves of the streaming kernels).  Measured ms per matrix at
+    4096^2 (profiles/r02_tri_*.log): 9 weights 44.2, 13 weights 45.0, 18 weights 44.3, 27 weights 40.4.
+    ASVD_B200_WAVES overrides the number of solve waves; at most 32 weights, bounded by the workspace budget."""
     _require_cuda()
     sms = torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device()).multi_processor_count
     pairs = (min(m, n) + 127) // 128
     lib = load()
     try:
-        waves = max(1, int(os.environ.get("ASVD_B200_WAVES", "4")))
+        waves = max(1, int(os.environ.get("ASVD_B200_WAVES", "2")))
     except ValueError:
-        waves = 4
+        waves = 2
+    waves *= SOLVE_CTAS_PER_SM
     b = int(max(1, min(waves * sms // max(pairs, 1), 32)))
     while b > 1 and lib.asvd_svd_workspace_bytes(int(m), int(n), b) > limit_bytes:      # part of the workspace is per call
         b -= 1

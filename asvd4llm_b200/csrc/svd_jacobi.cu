@@ -377,6 +377,28 @@ __device__ __forceinline__ bool solve_prologue(const float* __restrict__ Gpart, 
     // (NT threads: JK*JK/4/NT float4 per thread, in passes of 8 so that a 256-thread CTA stays within its registers;
     // every element still sums its chunks in the same order, whatever NT)
     const float4* Gp4 = reinterpret_cast<const float4*>(Gp);
+    if constexpr ((JK * JK / 4) % (NT * 8) != 0) {
+      // thread counts that do not divide the matrix (the 160-thread triangular solve): passes of 4, ragged tail guarded
+#pragma unroll 1
+      for (int base = tid; base < JK * JK / 4; base += NT * 4) {
+        float4 acc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < chunks; ++c) {
+          float4 v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            v[i] = (base + NT * i < JK * JK / 4) ? Gp4[(int64_t)c * (JK * JK / 4) + base + NT * i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { acc[i].x += v[i].x; acc[i].y += v[i].y; acc[i].z += v[i].z; acc[i].w += v[i].w; }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int e = (base + NT * i) * 4;
+          if (e < JK * JK) *reinterpret_cast<float4*>(&G[(e >> 7) * SLD + (e & (JK - 1))]) = acc[i];
+        }
+      }
+    } else
 #pragma unroll 1
     for (int pass = 0; pass < JK * JK / 4 / NT / 8; ++pass) {
       const int base = tid + NT * 8 * pass;
@@ -831,6 +853,7 @@ solve_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_mat, flo
 }
 
 #include "svd_solve_quad.cuh"
+#include "svd_solve_tri.cuh"
 
 // ------------------------------------------------------------------------------------------------ update
 // panel <- R^T panel, i.e. out[j][c] = sum_i R[i][j] * X[i][c], in place, UPD_TILES column tiles of 128 per CTA.
@@ -1205,6 +1228,10 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
     ASVD_CUDA_CHECK(cudaFuncSetAttribute(solve_quad_g_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVEQG_SMEM));
     ASVD_CUDA_CHECK(cudaFuncSetAttribute(solve_quad_g_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   // two CTAs per SM
     ASVD_CUDA_CHECK(cudaFuncSetAttribute(solve_quad_r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVEQR_SMEM));
+    ASVD_CUDA_CHECK(cudaFuncSetAttribute(solve_tri_g_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVET_SMEM));
+    ASVD_CUDA_CHECK(cudaFuncSetAttribute(solve_tri_g_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   // three CTAs per SM
+    ASVD_CUDA_CHECK(cudaFuncSetAttribute(solve_tri_r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVETR_SMEM));
+    ASVD_CUDA_CHECK(cudaFuncSetAttribute(solve_tri_r_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   // two CTAs per SM
     ASVD_CUDA_CHECK(upload_quad_schedule());
     ASVD_CUDA_CHECK(cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPDATE_SMEM));
     ASVD_CUDA_CHECK(cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 16384));
@@ -1264,8 +1291,9 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
       sms_dev = 148;
   }
   const bool lean_auto = auto_env && auto_env[0] == '1' && !solve_env && quad_pays && p.batch * p.pairs > sms_dev;
-  const bool solve_lean = !dbg_env && polish_flag == 2 && ((solve_env && solve_env[0] == 'l') || lean_auto);
-  const bool solve_quad = !dbg_env && !solve_lean && (solve_env ? solve_env[0] == 'q' : quad_pays);
+  const bool solve_tri = !dbg_env && polish_flag == 2 && (solve_env ? solve_env[0] == 't' : true);
+  const bool solve_lean = !dbg_env && !solve_tri && polish_flag == 2 && ((solve_env && solve_env[0] == 'l') || lean_auto);
+  const bool solve_quad = !dbg_env && !solve_tri && !solve_lean && (solve_env ? solve_env[0] == 'q' : quad_pays);
   const char* simt_env = getenv("ASVD_B200_SIMT");
   const bool use_tc = !(simt_env && simt_env[0] == '1');
   // Overlapped half-batches (ASVD_B200_OVERLAP=1).  The solve is a chain of 127 dependent rotation steps on one CTA per
@@ -1385,7 +1413,11 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
         }
         // the token: this half's solve starts when the other half's latest solve has finished
         if (n_parts == 2 && !(r == 0 && h == 0)) ASVD_CUDA_CHECK(cudaStreamWaitEvent(s, ev_solve[h ^ 1], 0));
-        if (solve_lean) {
+        if (solve_tri) {
+          float* auxq = reinterpret_cast<float*>(ws + p.off_aux) + (size_t)q.b0 * p.pairs * QAUX_FLOATS;
+          ASVD_LAUNCH(K_SOLVE, s, (solve_tri_g_kernel<<<dim3(p.pairs, q.nb), TRI_THREADS, SOLVET_SMEM, s>>>(Gq, p.chunks, p.pairs, auxq, flagq, maxoffq, statusq, doneq, tol, pr, trackq, p.nb, round_stamp, precq, half_gram)));
+          ASVD_LAUNCH(K_SOLVE, s, (solve_tri_r_kernel<<<dim3(p.pairs, q.nb), 256, SOLVETR_SMEM, s>>>(auxq, p.pairs, Rq, flagq, doneq)));
+        } else if (solve_lean) {
           float* auxq = reinterpret_cast<float*>(ws + p.off_aux) + (size_t)q.b0 * p.pairs * QAUX_FLOATS;
           ASVD_LAUNCH(K_SOLVE, s, (solve_quad_g_kernel<<<dim3(p.pairs, q.nb), 256, SOLVEQG_SMEM, s>>>(Gq, p.chunks, p.pairs, auxq, flagq, maxoffq, statusq, doneq, tol, pr, trackq, p.nb, round_stamp, precq, half_gram)));
           ASVD_LAUNCH(K_SOLVE, s, (solve_quad_r_kernel<<<dim3(p.pairs, q.nb), 256, SOLVEQR_SMEM, s>>>(auxq, p.pairs, Rq, flagq, doneq)));

@@ -247,7 +247,7 @@ def run_reference(args, rank, world):
 
 def _default_batch_static():
     """suggest_batch(4096, 4096) on a 148-SM part, without touching a GPU (the CPU arm prints the same config keys)."""
-    return 4 * 148 // 32
+    return 2 * 3 * 148 // 32
 
 
 def llama_cpu_estimate(O):

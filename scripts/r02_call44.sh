@@ -1,0 +1,8 @@
+set -x
+cd /root/repo
+timeout 300 python scripts/check_tri.py small 2>&1 | tee gpurun_out/r02_tri_small.log
+PROF_BATCH=9 timeout 300 python scripts/check_tri.py tri 2>&1 | tee gpurun_out/r02_tri_big.log
+PROF_BATCH=27 timeout 300 python scripts/check_tri.py tri 2>&1 | tee -a gpurun_out/r02_tri_big.log
+export ASVD_B200_SOLVE=tri PROF_BATCH=9 PROF_FORWARD=0 PROF_SWEEPS=2
+PROF='ncu --set full --clock-control none --import-source on'
+$PROF -k regex:solve_tri_r -s 40 -c 1 -o gpurun_out/p_tri_r -f python scripts/prof_one.py > gpurun_out/p_tri_r.log 2>&1

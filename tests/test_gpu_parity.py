@@ -478,9 +478,9 @@ def test_suggest_batch_fills_whole_waves(monkeypatch):
         for (m, n) in [(4096, 4096), (11008, 4096), (768, 768), (5120, 5120)]:
             b = L.suggest_batch(m, n)
             pairs = (min(m, n) + 127) // 128
-            assert 1 <= b <= 32 and b * pairs <= max(waves * sms, pairs)
+            assert 1 <= b <= 32 and b * pairs <= max(waves * L.SOLVE_CTAS_PER_SM * sms, pairs)
     monkeypatch.delenv("ASVD_B200_WAVES")
-    assert L.suggest_batch(4096, 4096) == min(32, 4 * sms // 32)            # the batch bench.py times
+    assert L.suggest_batch(4096, 4096) == min(32, 2 * L.SOLVE_CTAS_PER_SM * sms // 32)     # the batch bench.py times
     assert L.balanced_batches(128, 18) == [16] * 8 and L.balanced_batches(5, 18) == [5] and L.balanced_batches(19, 18) == [10, 9]
 
 
