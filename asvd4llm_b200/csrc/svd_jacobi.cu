@@ -384,13 +384,21 @@ __device__ __forceinline__ bool solve_prologue(const float* __restrict__ Gpart, 
         float4 acc[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int c = 0; c < chunks; ++c) {
-          float4 v[4];
+        // four chunks' loads (16 float4 per thread) in flight before the first add; chunks are still summed in order
+        for (int c0 = 0; c0 < chunks; c0 += 4) {
+          float4 v[4][4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            v[i] = (base + NT * i < JK * JK / 4) ? Gp4[(int64_t)c * (JK * JK / 4) + base + NT * i] : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int cc = 0; cc < 4; ++cc)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { acc[i].x += v[i].x; acc[i].y += v[i].y; acc[i].z += v[i].z; acc[i].w += v[i].w; }
+            for (int i = 0; i < 4; ++i)
+              v[cc][i] = (c0 + cc < chunks && base + NT * i < JK * JK / 4) ? Gp4[(int64_t)(c0 + cc) * (JK * JK / 4) + base + NT * i]
+                                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc)
+            if (c0 + cc < chunks) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { acc[i].x += v[cc][i].x; acc[i].y += v[cc][i].y; acc[i].z += v[cc][i].z; acc[i].w += v[cc][i].w; }
+            }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {

@@ -319,8 +319,8 @@ def svd_workload(ctx):
     from asvd4llm_b200.modules.svd_linear import from_linear_batch
     import torch.nn as nn
     args, dev, rank, world = ctx.args, ctx.dev, ctx.rank, ctx.world
-    # the batch the product's own final pass uses for this shape (binary_search._install -> suggest_batch): four waves
-    # of block pairs on the SMs (18 at 4096^2 on 148 SMs); --batch overrides for experiments
+    # the batch the product's own final pass uses for this shape (binary_search._install -> suggest_batch): two solve
+    # waves of 3 x SMs block pairs (27 at 4096^2 on 148 SMs); --batch overrides for experiments
     B = args.batch if args.batch > 0 else _lib.suggest_batch(M, N_IN, dev)
     r = _lib.rank_for_ratio(M, N_IN, RATIO, 1)
     g = torch.Generator(device=dev).manual_seed(233 + rank)
@@ -339,7 +339,7 @@ def svd_workload(ctx):
         return fact, outs
 
     clocks = ClockSampler(ctx.local).start()             # NVML start-up happens during the warm-up, not the timed region
-    # Every step drops the previous step's factorisation before it allocates its own workspace (4.6 GB at 18 weights), as a
+    # Every step drops the previous step's factorisation before it allocates its own workspace (6.9 GB at 27 weights), as a
     # pipeline that consumes the factors would: with two workspaces alive in turn the caching allocator sooner or later
     # splits the free one for the 15 MB factor tensors and has to cudaMalloc a fresh 4.6 GB block mid-run -- the "hiccup"
     # that kept landing on the second timed step (843 -> 900-1270 ms; profiles/r02_bench_hiccup.log).
@@ -441,7 +441,8 @@ def svd_workload(ctx):
         pairs, JK = nv // 128, 128
         x_bytes = B * nv * len_ * 4
         g_bytes = r_bytes = B * pairs * JK * JK * 4
-        impl = {"gram": x_bytes + g_bytes, "solve": g_bytes + r_bytes, "update": 2 * x_bytes + r_bytes}
+        aux_bytes = B * pairs * 67584                                   # per-pair rotation record: written by the G sweep, read by the replay
+        impl = {"gram": x_bytes + g_bytes, "solve": g_bytes + r_bytes + 2 * aux_bytes, "update": 2 * x_bytes + r_bytes}
         pk = peaks()
         peak = pk["hbm_gbs"]
         traffic, tsrc = {}, None
@@ -456,8 +457,8 @@ def svd_workload(ctx):
         for k in ("gram", "solve", "update"):
             us = classes[k]["ms"] / rounds * 1e3
             t_round += us
-            tk = {"gram": "gram_tc", "solve": "solve_quad", "update": "update_tc"}[k]
-            tv = traffic.get(tk)
+            tks = {"gram": ["gram_tc"], "solve": ["solve_tri_g", "solve_tri_r"], "update": ["update_tc"]}[k]
+            tv = sum(traffic[t] for t in tks) if all(t in traffic for t in tks) else None
             per_kernel[k] = {"us_per_round": round(us, 1), "launches_per_round": round(classes[k]["launches"] / rounds, 2),
                              "implementation_bytes": impl[k], "implementation_GBps": round(impl[k] / us / 1e3, 1),
                              "frac_of_hbm_peak_implementation_bytes": round(impl[k] / us / 1e3 / peak, 3),
@@ -475,8 +476,8 @@ def svd_workload(ctx):
                     "implementation_frac": impl_bytes / t_round / 1e3 / peak,
                     "avg_launch_us": round(t_round, 1),
                     "solve_share_of_round": round(per_kernel["solve"]["us_per_round"] / t_round, 3),
-                    "note": "the inner solve is an on-chip Jacobi eigensolver bounded by its 127 dependent rotation steps, not by HBM; "
-                            "gram/update are the streaming passes",
+                    "note": "the inner solve (solve_tri_g_kernel + solve_tri_r_kernel) is an on-chip Jacobi eigensolver bounded by its 127 "
+                            "dependent rotation steps, not by HBM; gram/update are the streaming passes",
                     "per_kernel": per_kernel,
                     "class_ms_first_2_sweeps": {k: round(v["ms"], 3) for k, v in classes.items()},
                     "class_ms_full_factorisation": full_run}

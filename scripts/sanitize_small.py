@@ -14,6 +14,9 @@ cases = [(512, 384, 2, "0"), (384, 640, 1, "0"), (2304, 1024, 1, "0"), (512, 512
 if os.environ.get("SAN_LEAN") == "1":           # the experimental lean solve (racecheck it before it becomes a default)
     os.environ["ASVD_B200_SOLVE"] = "lean"
     cases = [(512, 512, 2, "0"), (384, 640, 1, "0"), (1024, 1024, 3, "1"), (129, 65, 2, "0")]
+if os.environ.get("SAN_TRI") == "1":            # the default (triangular) solve alone: short list for racecheck / synccheck
+    os.environ.pop("ASVD_B200_SOLVE", None)
+    cases = [(512, 512, 2, "0"), (384, 640, 1, "0"), (1024, 1024, 3, "0"), (129, 65, 2, "0")]
 for (m, n, B, overlap) in cases:
     os.environ["ASVD_B200_OVERLAP"] = overlap
     Ws = [(torch.randn(m, n, device=dev, generator=g) * 0.02).half() for _ in range(B)]

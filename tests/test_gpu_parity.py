@@ -439,14 +439,15 @@ def test_rectangular_llama_shapes_reduced():
 
 
 def test_inner_orderings_and_tails_agree(monkeypatch):
-    """The two inner eigen-solvers (quad round-robin / odd-even) and the two tails (unit column norms /
-    Newton-Schulz) are different routes to the same factorisation: singular values and the truncated product agree."""
+    """The inner eigen-solvers (triangular with a parameter warp -- the default --, quad round-robin, odd-even) and the
+    two tails (unit column norms / Newton-Schulz) are different routes to the same factorisation: singular values and the
+    truncated product agree."""
     L = _lib()
     W, s = O.synthetic_weight(1024, 1024, seed=11)
     scale = (s ** 0.5 + 1e-6).float().cuda()
     ref = torch.linalg.svdvals(W.double().cuda() * scale.double())
     results = {}
-    for solve, polish in (("quad", "norm"), ("oddeven", "norm"), ("quad", "NS"), ("oddeven", "NS")):
+    for solve, polish in (("quad", "norm"), ("oddeven", "norm"), ("quad", "NS"), ("oddeven", "NS"), ("tri", "norm")):
         monkeypatch.setenv("ASVD_B200_SOLVE", solve)
         monkeypatch.setenv("ASVD_B200_POLISH", polish)
         f = L.scaled_svd([W.cuda()], [scale])
@@ -685,6 +686,56 @@ def test_lean_solve_matches_quad_bitwise(m, n, batch, monkeypatch):
         A1, B1 = ref.extract(min(m, n) // 2, "UV", torch.float16, b)
         A2, B2 = got.extract(min(m, n) // 2, "UV", torch.float16, b)
         assert torch.equal(A1, A2) and torch.equal(B1, B2)
+
+
+@pytest.mark.parametrize("m,n,batch", [(1024, 1024, 2), (768, 1280, 1), (2048, 2048, 4), (2304, 1024, 2), (200, 136, 3)])
+def test_tri_solve_default(m, n, batch, monkeypatch):
+    """The default inner solve (solve_tri_g_kernel: upper triangle of the Gram matrix, rotation parameters on a warp of
+    their own; solve_tri_r_kernel: barrier-free replay on R) against the quad kernel it replaces and against fp64:
+      * the default IS the triangular solve (same bits as ASVD_B200_SOLVE=tri), run-to-run bitwise reproducible;
+      * a weight's factors do not depend on its batch-mates (bitwise, where the Gram chunking coincides);
+      * singular values within 2e-5 of fp64 (and of the quad kernel's) on the kept half, truncated product on the
+        Eckart-Young floor like the quad kernel's."""
+    L = _lib()
+    Ws, Ss = [], []
+    for b in range(batch):
+        W, s = O.synthetic_weight(m, n, seed=80 + b)
+        Ws.append(W.cuda()); Ss.append((s ** 0.5 + 1e-6).float().cuda())
+    r = min(m, n) // 2
+    monkeypatch.delenv("ASVD_B200_SOLVE", raising=False)
+    dflt = L.scaled_svd(Ws, Ss)
+    monkeypatch.setenv("ASVD_B200_SOLVE", "tri")
+    tri = L.scaled_svd(Ws, Ss)
+    alone = L.scaled_svd(Ws[-1:], Ss[-1:])
+    monkeypatch.setenv("ASVD_B200_SOLVE", "quad")
+    quad = L.scaled_svd(Ws, Ss)
+    monkeypatch.delenv("ASVD_B200_SOLVE")
+    assert dflt.status == 0 and tri.status == 0 and dflt.sweeps == tri.sweeps
+    for b in range(batch):
+        assert torch.equal(dflt.sigma(b), tri.sigma(b))
+        A0, B0 = dflt.extract(r, "UV", torch.float16, b)
+        A1, B1 = tri.extract(r, "UV", torch.float16, b)
+        assert torch.equal(A0, A1) and torch.equal(B0, B1)
+        ref = torch.linalg.svdvals(Ws[b].double() * Ss[b].double())
+        sig = tri.sigma(b).double()
+        assert ((sig[:r] - ref[:r]).abs() / ref[:r]).max().item() < 2e-5
+        # both kernels' truncated products sit on the Eckart-Young floor (the products themselves may differ by more:
+        # the subspace at the cut of a clustered spectrum is ill-conditioned, the error of the best approximation is not)
+        floor = (ref[r:] ** 2).sum().sqrt().item()
+        for fact in (quad, tri):
+            Af, Bf = fact.extract(r, "UV", torch.float32, b)
+            rec = ((Af.double() @ Bf.double() - Ws[b].double()) * Ss[b].double()).norm().item()
+            assert rec <= floor * (1 + 1e-4) + 1e-6 * ref[0].item(), (rec, floor)
+        assert ((quad.sigma(b).double()[:r] - sig[:r]).abs() / ref[:r]).max().item() < 2e-5
+    # batch independence is bitwise whenever both batch sizes cut the long dimension into the same Gram chunks
+    # (make_plan: just enough chunks to give every SM an item, at least 512 columns each)
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    pairs, max_chunks = (min(m, n) + 127) // 128, (max(m, n) + 127) // 128 * 128 // 512 + (1 if (max(m, n) + 127) // 128 * 128 % 512 else 0)
+    if sms // (batch * pairs) >= max_chunks:
+        assert torch.equal(alone.sigma(0), tri.sigma(batch - 1))
+        Aa, Ba = alone.extract(r, "UV", torch.float16, 0)
+        Ab, Bb = tri.extract(r, "UV", torch.float16, batch - 1)
+        assert torch.equal(Aa, Ab) and torch.equal(Ba, Bb)
 
 
 # ------------------------------------------------------------------------------------------------ full-size shapes (§8d configs 3/5)
