@@ -1365,8 +1365,13 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
   float tol_pre = pre_env ? (float)atof(pre_env) : 5.f * tol;
   if (conv_tol > 0.f) tol_pre = conv_tol;          // experiments (ASVD_B200_INNER_TOL): looser tolerance for the square stage
   if (tol_pre < tol) tol_pre = tol;
+  // When a matrix leaves the single-pass TF32 Gram for the fp32-accurate one: after a sweep in which at least this share
+  // of its pair visits met cosines below 1e-2.  The accurate pass is no longer free (the split keeps four warps busy:
+  // 425 vs 289 us per launch at 27 x 4096^2) and only matters once MOST pairs are small; the first few pairs get there
+  // around sweep 4, the majority around sweep 7.  Measured (profiles/r02_ab_near_pct_tri*.jsonl): 0 / 50 / 70 / 80 %:
+  // 1120 / 1077 / 1074 / 1079 ms per 27 x 4096^2, same sweep counts and sigma errors; 2048^2 -3 %, 4096x11008 -2 %.
   const char* near_env = getenv("ASVD_B200_NEAR_PCT");
-  const unsigned near_min = near_env ? (unsigned)(atof(near_env) * 0.01 * p.rounds * p.pairs) : 0u;
+  const unsigned near_min = (unsigned)((near_env ? atof(near_env) : 50.0) * 0.01 * p.rounds * p.pairs);
   std::vector<unsigned> h_maxoff(2 * (size_t)p.batch);
   std::vector<int> h_done(p.batch, 0), h_sweeps(p.batch, 0);
   bool gave_up = false;

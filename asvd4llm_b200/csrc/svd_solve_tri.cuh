@@ -245,6 +245,12 @@ solve_tri_g_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_ma
 #pragma unroll 1
   for (int r = 0; r < QROUNDS; ++r) {
     const int s0 = 3 + 4 * r;
+    // what this round's move will do to this patch: looked up BEFORE the steps, while the off-diagonal warps would
+    // otherwise sit at the first step's barrier (the lookups are off the critical path of the round's end)
+    const unsigned char* qs = qsrc + (r < QROUNDS - 1 ? r : 0) * 32;
+    const int rsrcL = qs[2 * pa], rsrcH = qs[2 * pa + 1], csrcL = qs[2 * pc], csrcH = qs[2 * pc + 1];
+    const bool mrL = rsrcL != 8 * pa, mrH = rsrcH != 8 * pa + 4, mcL = csrcL != 8 * pc, mcH = csrcH != 8 * pc + 4;
+    const bool mv[4] = {mrL || mcL, mrL || mcH, mrH || mcL, mrH || mcH};
     TRI_STEP(3, s0 + 0, 4);
     TRI_STEP(4, s0 + 1, 5);
     TRI_STEP(5, s0 + 2, 6);
@@ -271,10 +277,6 @@ solve_tri_g_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_ma
       // (dfold is next written eight rounds later, behind many blocking barriers)
     }
     // ---- quad move through the staging area: only what changes place
-    const unsigned char* qs = qsrc + r * 32;
-    const int rsrcL = qs[2 * pa], rsrcH = qs[2 * pa + 1], csrcL = qs[2 * pc], csrcH = qs[2 * pc + 1];
-    const bool mrL = rsrcL != 8 * pa, mrH = rsrcH != 8 * pa + 4, mcL = csrcL != 8 * pc, mcH = csrcH != 8 * pc + 4;
-    const bool mv[4] = {mrL || mcL, mrL || mcH, mrH || mcL, mrH || mcH};
     if (writes) {
       if (is_param) {
         quad_stage_write_diag(G, g, pa, mv);
