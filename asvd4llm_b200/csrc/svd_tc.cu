@@ -11,7 +11,8 @@
 //   warp 1  MMA issuer (whole warp, one elected lane): 4 K-steps of tcgen05.mma M=128 N=128 K=8 per stage
 //   warp 2  TMEM allocator
 //   warps 4-7  epilogue: tcgen05.ld -> global partial Gram
-//   warps 8-11 split (precise mode): thread t owns row t of the landed tile; hi = rna_tf32(x) goes back in place, the
+//   warps 8-15 split (precise mode, two groups of four taking the tiles in turn): thread t owns row t of the landed tile;
+//              hi = rna_tf32(x) goes back in place, the
 //              A operand (0.5 hi | lo) goes to TENSOR MEMORY (tcgen05.st)
 // Precise mode computes only T = (0.5 HI + LO) HI^T -- two MMAs per K-step, A from tensor memory, B = the hi tile
 // in shared memory -- and the solve kernel forms G = T + T^T = HI HI^T + LO HI^T + HI LO^T.  Against three
@@ -31,7 +32,7 @@ constexpr int GR_HI_BYTES = 128 * 128;           // 128 rows x 32 floats
 constexpr int GR_BAR_OFFSET = GR_NH * GR_HI_BYTES;
 constexpr uint32_t GR_TMEM_A = 256;              // accumulators at columns 0 and 128, A ring from column 256
 constexpr int GR_SMEM = GR_BAR_OFFSET + 512 + 1024;
-constexpr int GR_THREADS = 384;
+constexpr int GR_THREADS = 512;               // 16 warps: TMA, MMA, TMEM alloc, (idle), 4 epilogue, 2 x 4 split
 
 __device__ __forceinline__ float rna_tf32(float x) {
   uint32_t r;
@@ -186,16 +187,25 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__
       if (lane == 0) mbar_arrive(&tempty[buf]);
     }
   } else if (warp >= 8 && precise) {
-    const int t = threadIdx.x - 256;                         // row of the tile = TMEM lane; warp 8+q owns lanes 32q..
-    const int q = warp - 8;
+    // Two groups of four split warps take the landed tiles in turn (group = stage parity).  One group alone has to get
+    // through load -> round -> store -> tcgen05.st -> wait -> fence -> arrive once per 16 KB tile, ~780 clocks at the
+    // HBM rate: measured, the accurate pass ran at 0.65 of the copy bandwidth against 0.9 for the single pass.
+    const int q = (warp - 8) & 3, grp = (warp - 8) >> 2;
+    const int t = q * 32 + lane;                             // row of the tile = TMEM lane; warps 8+q and 12+q own lanes 32q..
     int hs = 0; uint32_t hph = 0;
     int as = 0; uint32_t aph = 0;
+    int stage = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int b = item / per_mat, c = item % chunks;
       if (done[b] || precise_b[b] != precise) continue;   // the launch serves the matrices in ITS Gram mode
       { const int2 pr = pairs[(item % per_mat) / chunks]; if (pair_is_clean(track, nv_pad / JB, b, pr.x, pr.y)) continue; }
       const int k0 = c * chunk_cols, k1 = min(len_pad, k0 + chunk_cols);
-      for (int k = k0; k < k1; k += 32) {
+      for (int k = k0; k < k1; k += 32, ++stage) {
+        if ((stage & 1) != grp) {                            // the other group's tile: only the ring positions advance
+          if (++hs == GR_NH) { hs = 0; hph ^= 1; }
+          if (++as == GR_NA) { as = 0; aph ^= 1; }
+          continue;
+        }
         mbar_wait(&full[hs], hph);
         // row t of the 128-byte-swizzled tile: 16-byte chunk j lives at chunk j ^ (t & 7)
         unsigned char* row = smem + hs * GR_HI_BYTES + t * 128;
@@ -209,11 +219,15 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__
           float h[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            h[e] = rna_tf32(x[e]);
+            // hi = x with the 13 low mantissa bits cleared: exactly what the tensor core makes of the RAW tile it reads
+            // as the B operand (kind::tf32 ignores those bits), so nothing has to be written back to shared memory --
+            // the write-back of a rounded hi was a fifth of this mode's shared-memory traffic (80 KB moved per 16 KB
+            // landed, against 640 of the 780 clocks a stage has at the HBM rate).  lo = x - hi is exact; the dropped
+            // lo*lo term is <= 2^-20 per product with a common sign, i.e. ~3e-7 RELATIVE on a Gram entry.
+            h[e] = __uint_as_float(__float_as_uint(x[e]) & 0xffffe000u);
             hh[4 * j + e] = __float_as_uint(0.5f * h[e]);
             lo[4 * j + e] = __float_as_uint(x[e] - h[e]);
           }
-          *reinterpret_cast<float4*>(row + ((j ^ (t & 7)) << 4)) = make_float4(h[0], h[1], h[2], h[3]);
         }
         mbar_wait(&a_empty[as], aph ^ 1);
         tc_fence_after();
