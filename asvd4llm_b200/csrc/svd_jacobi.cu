@@ -107,6 +107,10 @@ SvdPlan make_plan(int m, int n, int batch, bool allow_inner) {
       cudaGetLastError();
     }
     int want = sms / (batch * p.pairs > 0 ? batch * p.pairs : 1);
+    // The chunking decides the summation order of a Gram entry, so a weight's factors are bitwise independent of its
+    // batch-mates exactly when the batch sizes compared cut the columns alike (always, from batch * pairs >= SMs on: one
+    // chunk).  ASVD_B200_GRAM_CHUNKS=n pins the count for runs that must reproduce each other at any batch size.
+    if (const char* ce = getenv("ASVD_B200_GRAM_CHUNKS")) { const int v = atoi(ce); if (v > 0) want = v; }
     const int max_chunks = (p.len_pad + 511) / 512;
     if (want < 1) want = 1;
     if (want > max_chunks) want = max_chunks;
@@ -120,7 +124,6 @@ SvdPlan make_plan(int m, int n, int batch, bool allow_inner) {
   p.off_X = take(sizeof(float) * (size_t)batch * p.nv_pad * p.len_pad);    // block-tiled (xt_off), the Jacobi working set
   p.off_Xr = take(sizeof(float) * (size_t)batch * p.nv_pad * p.len_pad);   // row-major copy made once after convergence
   p.off_Y = take(sizeof(float) * (size_t)batch * p.nv_pad * p.ldy);
-  p.off_G = take(sizeof(float) * (size_t)batch * p.pairs * p.chunks * JK * JK);
   p.off_R = take(sizeof(float) * (size_t)batch * p.pairs * JK * JK);
   p.off_flag = take(sizeof(int) * (size_t)batch * p.pairs);
   p.off_maxoff = take(sizeof(unsigned) * 2 * (size_t)batch);   // [batch] max cosine bits, [batch] near-converged pair counts
@@ -155,6 +158,9 @@ SvdPlan make_plan(int m, int n, int batch, bool allow_inner) {
   }
   // per-pair record of the lean solve (ASVD_B200_SOLVE=lean): rotation history, scales, column order (svd_solve_quad.cuh)
   p.off_aux = take(sizeof(float) * (size_t)batch * p.pairs * QAUX_FLOATS_PLAN);
+  // LAST: the only buffer whose size depends on the Gram chunking (hence, with ASVD_B200_GRAM_CHUNKS, on the environment
+  // at call time); asvd_svd_sigma / asvd_svd_extract re-derive the plan later and must find everything else in place
+  p.off_G = take(sizeof(float) * (size_t)batch * p.pairs * p.chunks * JK * JK);
   p.bytes = off;
   return p;
 }

@@ -738,6 +738,28 @@ def test_tri_solve_default(m, n, batch, monkeypatch):
         assert torch.equal(Aa, Ab) and torch.equal(Ba, Bb)
 
 
+def test_pinned_gram_chunks_make_every_batch_size_bitwise_equal(monkeypatch):
+    """The Gram pass cuts the long dimension into just enough chunks to give every SM an item, so the chunking -- hence
+    the summation order of a Gram entry -- depends on how many weights share the launch: 2048^2 alone runs four chunks,
+    in a batch of four two.  ASVD_B200_GRAM_CHUNKS pins the count; with it a weight's factors are bitwise the same alone
+    and in a batch (without it they agree to rounding: checked here too)."""
+    L = _lib()
+    m = n = 2048
+    Ws, Ss = [], []
+    for b in range(4):
+        W, s = O.synthetic_weight(m, n, seed=90 + b)
+        Ws.append(W.cuda()); Ss.append((s ** 0.5 + 1e-6).float().cuda())
+    loose_b, loose_a = L.scaled_svd(Ws, Ss), L.scaled_svd(Ws[2:3], Ss[2:3])
+    assert ((loose_b.sigma(2)[:900] - loose_a.sigma(0)[:900]).abs() / loose_a.sigma(0)[:900]).max().item() < 2e-5
+    monkeypatch.setenv("ASVD_B200_GRAM_CHUNKS", "2")
+    batch, alone = L.scaled_svd(Ws, Ss), L.scaled_svd(Ws[2:3], Ss[2:3])
+    monkeypatch.delenv("ASVD_B200_GRAM_CHUNKS")
+    assert torch.equal(batch.sigma(2), alone.sigma(0))
+    A1, B1 = batch.extract(900, "UV", torch.float16, 2)
+    A2, B2 = alone.extract(900, "UV", torch.float16, 0)
+    assert torch.equal(A1, A2) and torch.equal(B1, B2)
+
+
 # ------------------------------------------------------------------------------------------------ full-size shapes (§8d configs 3/5)
 FULL_SIZE_SHAPES = [(11008, 4096, 0.9), (4096, 11008, 0.9), (32000, 4096, 0.9), (13824, 5120, 0.95), (50272, 768, 0.9)]
 
