@@ -75,11 +75,17 @@ int asvd_scaling_vector(const void* sdm, const void* fisher, int stat_dtype, int
  *                      through the Gram pre-conditioner: sweeps of the square stage + sweeps of the main stage)
  * sigma and the second factor are recovered from the ORIGINAL weight after convergence (exact bf16-plane GEMM on the
  * tensor cores for 16-bit weights, fp32 SIMT GEMM otherwise), so they carry no accumulated rotation error.
- * Environment switches for A/B runs (read at every call): ASVD_B200_SOLVE=quad|oddeven, ASVD_B200_POLISH=NS,
- * ASVD_B200_GRAMPRE=0, ASVD_B200_RECOVER=simt, ASVD_B200_PRESORT=0, ASVD_B200_SIMT=1, ASVD_B200_TRACE=1,
- * ASVD_B200_OVERLAP=1 (two half-batches on two internal streams; same results bitwise, measured not faster),
- * ASVD_B200_SOLVE=lean (experimental split of the inner sweep: G-only kernel at two CTAs per SM + R replay kernel;
- * ASVD_B200_LEAN_AUTO=1 selects it only where a batch has more block pairs than the device has SMs).
+ * The inner eigen-solve of a block pair is the triangular kernel pair (solve_tri_g_kernel: upper triangle of the Gram
+ * matrix, rotation parameters on a warp of their own, three pairs per SM; solve_tri_r_kernel: replay of the rotation
+ * record on R).  A weight's factors are bitwise reproducible run to run; they are bitwise independent of its batch-mates
+ * whenever the batches compared cut the Gram pass into the same column chunks (always from batch * pairs >= SMs on);
+ * ASVD_B200_GRAM_CHUNKS=n pins the chunk count where that must hold at any batch size.
+ * Environment switches for A/B runs (read at every call): ASVD_B200_SOLVE=tri|quad|oddeven|lean (tri is the default;
+ * quad / oddeven: the second- / first-generation single-kernel solves; lean: the quad kernel split in a G-only kernel at
+ * two CTAs per SM + replay), ASVD_B200_POLISH=NS, ASVD_B200_GRAMPRE=0, ASVD_B200_RECOVER=simt, ASVD_B200_PRESORT=0,
+ * ASVD_B200_SIMT=1, ASVD_B200_TRACE=1, ASVD_B200_NEAR_PCT=p (share of a sweep's pair visits below 1e-2 after which a
+ * matrix takes the accurate Gram pass; default 50), ASVD_B200_OVERLAP=1 (two half-batches on two internal streams; same
+ * results bitwise, measured not faster).
  * Blocks the calling thread until the factorisation is complete on `stream` (it polls a convergence flag
  * once per sweep). */
 size_t asvd_svd_workspace_bytes(int m, int n, int batch);

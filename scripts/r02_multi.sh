@@ -1,0 +1,6 @@
+set -x
+cd /root/repo
+N=$1
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 --no-extras > gpurun_out/r02_bench_${N}gpu.json 2> gpurun_out/r02_bench_${N}gpu.err; echo rc=$?
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --workload llama7b > gpurun_out/r02_bench_llama7b_${N}gpu.json 2> gpurun_out/r02_bench_llama7b_${N}gpu.err; echo rc=$?
+tail -c 400 gpurun_out/r02_bench_${N}gpu.json; tail -c 900 gpurun_out/r02_bench_llama7b_${N}gpu.json
