@@ -208,10 +208,12 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__
         }
         mbar_wait(&full[hs], hph);
         // row t of the 128-byte-swizzled tile: 16-byte chunk j lives at chunk j ^ (t & 7)
-        unsigned char* row = smem + hs * GR_HI_BYTES + t * 128;
+        const uint32_t row = smem_u32(smem + hs * GR_HI_BYTES + t * 128);
         float4 v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(row + ((j ^ (t & 7)) << 4));
+        for (int j = 0; j < 8; ++j)      // explicit shared-space loads (the 1 KB-aligned base is computed through an integer: generic otherwise)
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(v[j].x), "=f"(v[j].y), "=f"(v[j].z), "=f"(v[j].w) : "r"(row + ((j ^ (t & 7)) << 4)));
         uint32_t hh[32], lo[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -235,8 +237,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmX, const int2* __restrict__
         tmem_st_32x32b_x32(a_tmem, hh);
         tmem_st_32x32b_x32(a_tmem + 32, lo);
         tmem_st_wait();
-        fence_proxy_async_smem();
-        tc_fence_before();
+        tc_fence_before();                                   // (no proxy fence: this mode no longer writes shared memory)
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_ready[as]);
         if (++hs == GR_NH) { hs = 0; hph ^= 1; }
