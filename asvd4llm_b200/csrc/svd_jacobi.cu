@@ -1439,6 +1439,11 @@ static int run_svd(const SvdPlan& p, int64_t ldw, unsigned char* ws, float tol, 
         } else if (solve_lean) {
           float* auxq = reinterpret_cast<float*>(ws + p.off_aux) + (size_t)q.b0 * p.pairs * QAUX_FLOATS;
           ASVD_LAUNCH(K_SOLVE, s, (solve_quad_g_kernel<<<dim3(p.pairs, q.nb), 256, SOLVEQG_SMEM, s>>>(Gq, p.chunks, p.pairs, auxq, flagq, maxoffq, statusq, doneq, tol, pr, trackq, p.nb, round_stamp, precq, half_gram)));
+          // ASVD_B200_SOLVE=leanr: the same G kernel with the triangular solve's replay kernel -- the bitwise bridge between
+          // solve_tri_r_kernel and the monolithic quad kernel (tests)
+          if (solve_env && solve_env[0] == 'l' && solve_env[1] == 'e' && solve_env[2] == 'a' && solve_env[3] == 'n' && solve_env[4] == 'r')
+            ASVD_LAUNCH(K_SOLVE, s, (solve_tri_r_kernel<<<dim3(p.pairs, q.nb), 256, SOLVETR_SMEM, s>>>(auxq, p.pairs, Rq, flagq, doneq)));
+          else
           ASVD_LAUNCH(K_SOLVE, s, (solve_quad_r_kernel<<<dim3(p.pairs, q.nb), 256, SOLVEQR_SMEM, s>>>(auxq, p.pairs, Rq, flagq, doneq)));
         } else if (solve_quad)
           ASVD_LAUNCH(K_SOLVE, s, (solve_quad_kernel<<<dim3(p.pairs, q.nb), SOLVE_THREADS, SOLVEQ_SMEM, s>>>(Gq, p.chunks, p.pairs, Rq, flagq, maxoffq, statusq, doneq, tol, polish_flag, pr, trackq, p.nb, round_stamp, precq, half_gram)));
