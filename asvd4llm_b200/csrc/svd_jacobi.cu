@@ -374,10 +374,11 @@ template <int NT = SOLVE_THREADS>
 __device__ __forceinline__ bool solve_prologue(const float* __restrict__ Gpart, int chunks, int idx, int b, int2 pr, int tid,
                                                float* G, float* red, int* __restrict__ pairflag,
                                                unsigned* __restrict__ maxoff_bits, int* __restrict__ status, float tol,
-                                               int* trk, int nb, int round_stamp, int precise, int nbatch, int half_gram) {
+                                               int* trk, int nb, int round_stamp, int precise, int nbatch, int half_gram,
+                                               bool preloaded = false) {
   const float* Gp = Gpart + (int64_t)idx * chunks * (JK * JK);
 
-  {
+  if (!preloaded) {     // (preloaded: the caller has already brought a single-chunk Gram matrix into G by bulk copies)
     // G = sum of the partial Grams.  16384 elements over 512 threads = 8 float4 per thread and chunk; all loads of
     // a chunk are issued before the first add so ~32 KB per warp are in flight
     // (NT threads: JK*JK/4/NT float4 per thread, in passes of 8 so that a 256-thread CTA stays within its registers;
@@ -1771,6 +1772,11 @@ int asvd_version(void) { return ASVD_B200_VERSION; }
 #ifdef ASVD_SOLVE_TIMING
 int asvd_debug_solve_timing(unsigned long long* out8) {       // timing builds only (scripts/solve_timing.py)
   return cudaMemcpyFromSymbol(out8, asvd::g_solve_timing, 8 * sizeof(unsigned long long)) == cudaSuccess ? 0 : 1;
+}
+#endif
+#ifdef ASVD_SOLVE_TIMING
+int asvd_debug_tri_timing(unsigned long long* out16) {         // timing builds only (scripts/tri_timing.py)
+  return cudaMemcpyFromSymbol(out16, asvd::g_tri_timing, 16 * sizeof(unsigned long long)) == cudaSuccess ? 0 : 1;
 }
 #endif
 const char* asvd_last_error(void) { return asvd::last_error(); }

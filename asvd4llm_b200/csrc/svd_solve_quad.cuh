@@ -182,6 +182,9 @@ __device__ __forceinline__ float* quad_stage(float* st, int pos, int chunk) { re
 // the dominant cost of the sweep after the dependent chain, and a sub-block whose row quad and column quad both stay
 // never goes through shared memory.
 __constant__ unsigned char c_quad_src[(QROUNDS - 1) * 32];
+// the same table in global memory: lanes copy it to shared memory with DIFFERENT indices, which a constant bank
+// serialises (8 % of the replay kernel's samples were that copy); 240 coalesced words instead
+__device__ unsigned int g_quad_src_words[(QROUNDS - 1) * 8];
 
 static bool build_quad_schedule(unsigned char* tab /* [(QROUNDS-1)*32] */) {
   int cur[32];                                   // quad id at slot 2g + h
@@ -229,6 +232,7 @@ static cudaError_t upload_quad_schedule() {
   unsigned char tab[(QROUNDS - 1) * 32];
   if (!build_quad_schedule(tab)) return cudaErrorUnknown;
   cudaError_t e = cudaMemcpyToSymbol(c_quad_src, tab, sizeof(tab));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_quad_src_words, tab, sizeof(tab));
   if (e == cudaSuccess) done[dev] = true;
   return e;
 }

@@ -18,6 +18,13 @@
 // receives.  The diagonal lanes keep full 8x8 patches (both triangles, rotated independently), so after a move an
 // element may descend from either copy: they agree to rounding, and the kernel is deterministic.
 constexpr int TRI_THREADS = 160;
+#ifdef ASVD_SOLVE_TIMING
+// timing build (scripts/tri_timing.py): clock64 marks of lane 0 of CTA (0,0); [0..7] G kernel, [8..15] replay kernel
+__device__ unsigned long long g_tri_timing[16];
+#define TT_MARK(cond, slot, t_last) do { if (cond) { const long long _t = clock64(); g_tri_timing[slot] += (unsigned long long)(_t - (t_last)); (t_last) = _t; } } while (0)
+#else
+#define TT_MARK(cond, slot, t_last) do { } while (0)
+#endif
 constexpr size_t SOLVET_SMEM = SOLVEQG_SMEM + sizeof(float4) * QRING * 16;
 
 // the transposed image of the sub-blocks that move: row 8pc + j of patch (pc, pa) is column j of patch (pa, pc)
@@ -186,10 +193,33 @@ solve_tri_g_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_ma
     if (tid == 0) pairflag[idx] = 0;
     return;
   }
-  for (int i = tid; i < (QROUNDS - 1) * 32; i += TRI_THREADS) qsrc[i] = c_quad_src[i];
+#ifdef ASVD_SOLVE_TIMING
+  const bool tt = tid == 0 && blockIdx.x == 0 && blockIdx.y == 0;
+  long long tt_last = clock64();
+  if (tt) for (int i = 0; i < 8; ++i) g_tri_timing[i] = 0;
+#endif
+  for (int i = tid; i < (QROUNDS - 1) * 8; i += TRI_THREADS) reinterpret_cast<unsigned int*>(qsrc)[i] = g_quad_src_words[i];
   const int precise = precise_b[b], half_gram = half_gram_tc && precise;
+  // One chunk (every batch with at least as many pairs as SMs): nothing to sum -- the 128 rows of the Gram matrix come in
+  // by 128 bulk copies of 512 bytes straight into the padded rows of G, one mbarrier.  (The generic path keeps four
+  // 16-byte loads per thread in flight: 12 % of this kernel's clocks at 27 x 4096^2, profiles/r02_tri_timing.log.)
+  __shared__ __align__(8) uint64_t pro_bar;
+  const bool preloaded = chunks == 1;
+  if (preloaded) {
+    if (tid == 0) { tc::mbar_init(&pro_bar, 1); tc::fence_barrier_init(); }
+    __syncthreads();
+    if (tid < JK) {
+      const float* src = Gpart + (int64_t)idx * (JK * JK) + tid * JK;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       tc::smem_u32(G + tid * SLD)),
+                   "l"(src), "r"((uint32_t)(JK * sizeof(float))), "r"(tc::smem_u32(&pro_bar))
+                   : "memory");
+    }
+    if (tid == 0) tc::mbar_arrive_expect_tx(&pro_bar, (uint32_t)(JK * JK * sizeof(float)));
+    tc::mbar_wait(&pro_bar, 0);
+  }
   if (!solve_prologue<TRI_THREADS>(Gpart, chunks, idx, b, pr, tid, G, red, pairflag, maxoff_bits, status, tol, trk, nb,
-                                   round_stamp, precise, gridDim.y, half_gram))
+                                   round_stamp, precise, gridDim.y, half_gram, preloaded))
     return;
 
   float* ax = aux + (int64_t)idx * QAUX_FLOATS;
@@ -227,6 +257,7 @@ solve_tri_g_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_ma
   for (int i = 0; i < 8; ++i) d[i] = 1.f;
   auto bar_all = [] { asm volatile("bar.sync 2, %0;" ::"n"(TRI_THREADS) : "memory"); };
   bar_all();                                                // every patch is in registers: G becomes the staging area
+  TT_MARK(tt, 0, tt_last);                                  // prologue
 
 #define TRI_STEP0(TYPE, S, BAR)                                                                             \
   do {                                                                                                      \
@@ -242,6 +273,7 @@ solve_tri_g_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_ma
   TRI_STEP0(0, 0, 8);
   TRI_STEP0(1, 1, 9);
   TRI_STEP0(2, 2, 10);
+  TT_MARK(tt, 1, tt_last);                                  // first three steps
 #pragma unroll 1
   for (int r = 0; r < QROUNDS; ++r) {
     const int s0 = 3 + 4 * r;
@@ -255,6 +287,7 @@ solve_tri_g_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_ma
     TRI_STEP(4, s0 + 1, 5);
     TRI_STEP(5, s0 + 2, 6);
     TRI_STEP(6, s0 + 3, 7);
+    TT_MARK(tt, 2, tt_last);                                // the parameter warp's four steps
     if (r == QROUNDS - 1) break;
     if ((r & 7) == 7) {
       // fold the deferred scales back into the stored values; the replay kernel folds the same values into R
@@ -276,6 +309,7 @@ solve_tri_g_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_ma
         for (int j = 0; j < 8; ++j) g[i][j] *= dr[i] * dc[j];
       // (dfold is next written eight rounds later, behind many blocking barriers)
     }
+    TT_MARK(tt, 3, tt_last);                                // fold
     // ---- quad move through the staging area: only what changes place
     if (writes) {
       if (is_param) {
@@ -287,12 +321,23 @@ solve_tri_g_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_ma
         quad_stage_write_t(G, g, pa, pc, mv);
       }
     }
+    TT_MARK(tt, 4, tt_last);                                // its staging writes
     bar_all();
-    quad_stage_read(G, g, rsrcL, rsrcH, csrcL, csrcH, mv);
+    TT_MARK(tt, 5, tt_last);                                // waiting for the off-diagonal warps at the move barrier
+    // The parameter warp reads first: its new diagonal patches head the next round's chain, the off-diagonal warps have a
+    // whole step of slack before they need theirs (they follow on barrier 3 instead of crowding the shared-memory pipe)
     if (is_param) {
+      quad_stage_read(G, g, rsrcL, rsrcH, csrcL, csrcH, mv);
 #pragma unroll
       for (int i = 0; i < 8; ++i) d[i] = dmov[(i < 4 ? rsrcL : rsrcH) + (i & 3)];
+      asm volatile("" ::"f"(g[0][0]), "f"(g[0][7]), "f"(g[7][7]), "f"(d[0]), "f"(d[7]) : "memory");   // the loads have landed
+      __syncwarp();
+      asm volatile("bar.arrive 3, %0;" ::"n"(TRI_THREADS) : "memory");
+    } else {
+      asm volatile("bar.sync 3, %0;" ::"n"(TRI_THREADS) : "memory");
+      quad_stage_read(G, g, rsrcL, rsrcH, csrcL, csrcH, mv);
     }
+    TT_MARK(tt, 6, tt_last);                                // its staging reads
     // no second barrier: the next write of the staging area (and of dmov) lies behind the next round's first step
     // barrier, at which the parameter warp WAITS and every off-diagonal thread arrives after these reads
   }
@@ -312,6 +357,7 @@ solve_tri_g_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_ma
     }
     a_dest[tid] = rank;
   }
+  TT_MARK(tt, 7, tt_last);                                  // tail
 }
 
 // solve_tri_r_kernel: replay of a pair's rotation record on R, without a staging area and without barriers in the loop.
@@ -331,12 +377,31 @@ constexpr int RCHUNKS = (QSTEPS + RCHUNK - 1) / RCHUNK;
 constexpr size_t SOLVETR_SMEM = sizeof(float) * (JK * SLD) + sizeof(float) * JK * (QFOLDS + 1) + sizeof(int) * JK + (QROUNDS - 1) * 32;
 static_assert(sizeof(float2) * QSTEPS * 64 <= sizeof(float) * JK * SLD, "the record must fit the sorted-R buffer");
 
+// Packed FP32 pairs (fma.rn.f32x2): measured on this part (scripts/probes/ffma2_replay_probe.cu) the replay's inner loop
+// takes 325 clocks per step with scalar FFMA and 163 with FFMA2 -- the packed instruction issues at the scalar rate.
+// The patch is held TRANSPOSED, rp[j][k] = (R[2k][j], R[2k+1][j]): a column rotation touches whole columns, so both
+// halves of a pair see the same multiplier.  Each half is the fma.rn the scalar code performs: results are bitwise equal.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+
 template <int TYPE>
-__device__ __forceinline__ void tri_r_step(float (&r)[8][8], const float2* hist, int step, int pc, uint64_t* mb) {
+__device__ __forceinline__ void tri_r_step(f32x2 (&rp)[8][4], const float2* hist, int step, int pc, uint64_t* mb) {
   if ((step & (RCHUNK - 1)) == 0) tc::mbar_wait(&mb[step / RCHUNK], 0);
   float2 q[4];
   load_q4(hist + step * 64, pc, q);
-  quad_cols<TYPE>(r, q);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int p = qp_p(TYPE, k), r = qp_q(TYPE, k);
+    const f32x2 X = pk2(q[k].x, q[k].x), Y = pk2(q[k].y, q[k].y);
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const f32x2 a = rp[p][h], b = rp[r][h];
+      rp[p][h] = ffma2(X, b, a);
+      rp[r][h] = ffma2(Y, a, b);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256, 2)
@@ -357,6 +422,11 @@ solve_tri_r_kernel(const float* __restrict__ aux, int pairs_per_mat, float* __re
   if (!pairflag[idx]) return;                               // clean, converged or non-finite pair: no rotation, no R
   const int tid = threadIdx.x, lane = tid & 31;
   const float* ax = aux + (int64_t)idx * QAUX_FLOATS;
+#ifdef ASVD_SOLVE_TIMING
+  const bool tt = tid == 0 && blockIdx.x == 0 && blockIdx.y == 0;
+  long long tt_last = clock64();
+  if (tt) for (int i = 8; i < 16; ++i) g_tri_timing[i] = 0;
+#endif
   if (tid == 0) {
     for (int c = 0; c < RCHUNKS; ++c) tc::mbar_init(&mb[c], 1);
     tc::fence_barrier_init();
@@ -374,18 +444,20 @@ solve_tri_r_kernel(const float* __restrict__ aux, int pairs_per_mat, float* __re
     const float4* src = reinterpret_cast<const float4*>(ax + (size_t)QSTEPS * 128);
     float4* dst = reinterpret_cast<float4*>(dhist);         // dhist | dfin | dest are contiguous in the record and here
     for (int i = tid; i < (QFOLDS + 2) * JK / 4; i += 256) dst[i] = src[i];
-    for (int i = tid; i < (QROUNDS - 1) * 32; i += 256) qsrc[i] = c_quad_src[i];
+    for (int i = tid; i < (QROUNDS - 1) * 8; i += 256) reinterpret_cast<unsigned int*>(qsrc)[i] = g_quad_src_words[i];
   }
   // patch (pa, pc): the 16 column groups of a row group in the 16 lanes of a half-warp
   const int pa = 2 * (tid >> 5) + (lane >> 4), pc = lane & 15;
   const float2* hist = reinterpret_cast<const float2*>(Rs);
-  float r[8][8];
+  f32x2 r[8][4];                                            // r[j][h] = (R[8pa + 2h][8pc + j], R[8pa + 2h + 1][8pc + j])
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int j = 0; j < 8; ++j)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r[i][j] = (pa == pc && i == j) ? 1.f : 0.f;
+    for (int h = 0; h < 4; ++h) r[j][h] = pk2((pa == pc && 2 * h == j) ? 1.f : 0.f, (pa == pc && 2 * h + 1 == j) ? 1.f : 0.f);
   __syncthreads();                                          // barriers initialised, scales and schedule in place
+  TT_MARK(tt, 8, tt_last);                                  // prologue
   tri_r_step<0>(r, hist, 0, pc, mb);
+  TT_MARK(tt, 9, tt_last);                                  // first step incl. waiting for the first chunk of the record
   tri_r_step<1>(r, hist, 1, pc, mb);
   tri_r_step<2>(r, hist, 2, pc, mb);
 #pragma unroll 1
@@ -395,6 +467,7 @@ solve_tri_r_kernel(const float* __restrict__ aux, int pairs_per_mat, float* __re
     tri_r_step<4>(r, hist, s0 + 1, pc, mb);
     tri_r_step<5>(r, hist, s0 + 2, pc, mb);
     tri_r_step<6>(r, hist, s0 + 3, pc, mb);
+    TT_MARK(tt, 10, tt_last);                               // four steps
     if (rd == QROUNDS - 1) break;
     if ((rd & 7) == 7) {
       const float* dh = dhist + (rd >> 3) * JK;
@@ -402,7 +475,7 @@ solve_tri_r_kernel(const float* __restrict__ aux, int pairs_per_mat, float* __re
       for (int j = 0; j < 8; ++j) {
         const float dc = dh[8 * pc + j];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) r[i][j] *= dc;
+        for (int h = 0; h < 4; ++h) { float a, b; upk2(r[j][h], a, b); r[j][h] = pk2(a * dc, b * dc); }
       }
     }
     // ---- quad move by shuffles inside the half-warp
@@ -413,29 +486,42 @@ solve_tri_r_kernel(const float* __restrict__ aux, int pairs_per_mat, float* __re
       // only H quads move, and they come from H slots
       const int src = (lane & 16) | (csrcH >> 3);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int j = 4; j < 8; ++j)
 #pragma unroll
-        for (int j = 4; j < 8; ++j) r[i][j] = __shfl_sync(0xffffffffu, r[i][j], src);
+        for (int h = 0; h < 4; ++h) {
+          float a, b; upk2(r[j][h], a, b);
+          r[j][h] = pk2(__shfl_sync(0xffffffffu, a, src), __shfl_sync(0xffffffffu, b, src));
+        }
     } else {
       // the halves regroup: an H slot takes the L quad of its partner group, whose L slot takes this H quad
       const int src = (lane & 16) | ((mcH ? csrcH : mcL ? csrcL : 8 * pc) >> 3);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float a = __shfl_sync(0xffffffffu, r[i][j], src), c = __shfl_sync(0xffffffffu, r[i][4 + j], src);
-          if (mcH) r[i][4 + j] = a;
-          if (mcL) r[i][j] = c;
+        for (int h = 0; h < 4; ++h) {
+          float l0, l1, h0, h1;
+          upk2(r[j][h], l0, l1); upk2(r[4 + j][h], h0, h1);
+          const float a0 = __shfl_sync(0xffffffffu, l0, src), a1 = __shfl_sync(0xffffffffu, l1, src);
+          const float c0 = __shfl_sync(0xffffffffu, h0, src), c1 = __shfl_sync(0xffffffffu, h1, src);
+          if (mcH) r[4 + j][h] = pk2(a0, a1);
+          if (mcL) r[j][h] = pk2(c0, c1);
         }
     }
+    TT_MARK(tt, 11, tt_last);                               // fold + move
   }
+  TT_MARK(tt, 12, tt_last);
   __syncthreads();                                          // everybody is done with the record: its buffer becomes R
+  TT_MARK(tt, 13, tt_last);                                 // waiting for the other warps
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int col = dest[8 * pc + j];
     const float dc = dfin[8 * pc + j];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) Rs[(8 * pa + i) * SLD + col] = r[i][j] * dc;
+    for (int h = 0; h < 4; ++h) {
+      float a, b; upk2(r[j][h], a, b);
+      Rs[(8 * pa + 2 * h) * SLD + col] = a * dc;
+      Rs[(8 * pa + 2 * h + 1) * SLD + col] = b * dc;
+    }
   }
   __syncthreads();
   // unit column norms (the default tail of solve_polish_write, same partial sums in the same order), then store
@@ -461,4 +547,5 @@ solve_tri_r_kernel(const float* __restrict__ aux, int pairs_per_mat, float* __re
     const float4 n = *reinterpret_cast<const float4*>(&cnp[0][c]);
     *reinterpret_cast<float4*>(&Ro[e]) = make_float4(x.x * n.x, x.y * n.y, x.z * n.z, x.w * n.w);
   }
+  TT_MARK(tt, 14, tt_last);                                 // sort, norms, store
 }
