@@ -12,7 +12,9 @@
 //   * data moves only once per ROUND (4 steps): a recursive tournament over the 32 quads (c_quad_src) moves whole quads
 //     between patches through shared memory, at most half of them per move.
 // Schedule: 3 steps inside the quads ((0,1)(2,3) / (0,2)(1,3) / (0,3)(1,2)), then 31 rounds of 4 steps pairing
-// L_i with H_(i+j)%4, j = 0..3: 127 steps, every pair of positions exactly once.
+// L_i with H_(i^j), j = 0..3 (XOR rather than a cyclic shift: the partners of the column pairs (0,1) and (2,3) are then
+// always a column PAIR, (4,5) or (6,7), in order or swapped -- what the packed FMAs of the triangular solve need):
+// 127 steps, every pair of positions exactly once.
 // The accumulated rotation R is kept by the other 256 threads as 8x8 patches too (column operations only).  They do
 // not take part in the G barriers: every step's parameters stay in a shared-memory history and the R threads follow
 // behind at their own pace (one single-use mbarrier per step says "published"), filling the issue slots the G threads leave.
@@ -25,13 +27,13 @@ constexpr int QFOLDS = 3;                      // after rounds 7, 15, 23
 constexpr size_t SOLVEQ_SMEM = sizeof(float) * (2 * JK * SLD) + sizeof(float2) * QSTEPS * 64 + sizeof(float) * 64 +
                                sizeof(int) * JK + sizeof(float) * JK * (3 + QFOLDS) + sizeof(uint64_t) * (QSTEPS + 1) + (QROUNDS - 1) * 32;
 
-// local positions (p, q) of pair k in a step of the given type: 0-2 inside the quads, 3-6 = L_i with H_(i+type-3)%4
+// local positions (p, q) of pair k in a step of the given type: 0-2 inside the quads, 3-6 = L_i with H_(i ^ (type-3))
 __host__ __device__ constexpr int qp_p(int type, int k) { return type == 0 ? 2 * k : type <= 2 ? (k < 2 ? k : k + 2) : k; }
 __host__ __device__ constexpr int qp_q(int type, int k) {
   return type == 0 ? 2 * k + 1
        : type == 1 ? (k < 2 ? k + 2 : k + 4)
        : type == 2 ? (k == 0 ? 3 : k == 1 ? 2 : k == 2 ? 7 : 6)
-                   : 4 + ((k + type - 3) & 3);
+                   : 4 + (k ^ (type - 3));
 }
 
 __device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }

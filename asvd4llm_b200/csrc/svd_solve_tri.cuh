@@ -158,6 +158,61 @@ __device__ __forceinline__ void tri_param_step(float (&g)[8][8], float (&d)[8], 
   tri_diag_apply<TYPE>(g, q);
 }
 
+// Packed FP32 pairs (fma.rn.f32x2): measured on this part (scripts/probes/ffma2_replay_probe.cu) the replay's inner loop
+// takes 325 clocks per step with scalar FFMA and 163 with FFMA2 -- the packed instruction issues at the scalar rate.
+// The patch is held TRANSPOSED, rp[j][k] = (R[2k][j], R[2k+1][j]): a column rotation touches whole columns, so both
+// halves of a pair see the same multiplier.  Each half is the fma.rn the scalar code performs: results are bitwise equal.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+
+// An off-diagonal patch in packed form for the four steps of a round: gp[i][c] = (g[i][2c], g[i][2c+1]).  Row rotations
+// pair along the columns (one multiplier for both halves); column rotations take the pivots two at a time -- columns
+// (0,1) with their partners, columns (2,3) with theirs: with the XOR schedule the partners are the pair (4,5) or (6,7), in
+// order for even steps and swapped for odd ones (the swap is an operand modifier of FFMA2, not an instruction).  Each
+// half is the fma.rn of quad_rows / quad_cols: same bits, 64 packed instructions instead of 128.
+__device__ __forceinline__ f32x2 swp2(f32x2 v) { float a, b; upk2(v, a, b); return pk2(b, a); }
+
+template <int TYPE>
+__device__ __forceinline__ void tri_bulk_step_packed(f32x2 (&gp)[8][4], const float2* cs_step, int pa, int pc, int bar_id) {
+  static_assert(TYPE >= 3, "packed form: steps of the rounds only");
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(TRI_THREADS) : "memory");
+  float2 qr[4], qc[4];
+  load_q4(cs_step, pa, qr);
+  load_q4(cs_step, pc, qc);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int p = qp_p(TYPE, k), r = qp_q(TYPE, k);
+    const f32x2 X = pk2(qr[k].x, qr[k].x), Y = pk2(qr[k].y, qr[k].y);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const f32x2 a = gp[p][c], b = gp[r][c];
+      gp[p][c] = ffma2(X, b, a);
+      gp[r][c] = ffma2(Y, a, b);
+    }
+  }
+  constexpr int M = TYPE - 3;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {                    // pivots (2h, 2h+1): column pair h with partner pair cH
+    constexpr bool SW = (M & 1) != 0;
+    const int cH = 2 + ((h ^ (M >> 1)) & 1);
+    f32x2 X = pk2(qc[2 * h].x, qc[2 * h + 1].x), Y = pk2(qc[2 * h].y, qc[2 * h + 1].y);
+    if (SW) Y = swp2(Y);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const f32x2 u = gp[i][h], v = gp[i][cH];
+      if (!SW) {
+        gp[i][h] = ffma2(X, v, u);
+        gp[i][cH] = ffma2(Y, u, v);
+      } else {
+        gp[i][h] = ffma2(X, swp2(v), u);
+        gp[i][cH] = ffma2(Y, swp2(u), v);
+      }
+    }
+  }
+}
+
 template <int TYPE>
 __device__ __forceinline__ void tri_bulk_step(float (&g)[8][8], const float2* cs_step, int pa, int pc, int bar_id) {
   asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(TRI_THREADS) : "memory");
@@ -244,116 +299,161 @@ solve_tri_g_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_ma
     else          { pa = lt & 7;  pc = pa + 8; }
     writes = lt < 120;
   }
-  float g[8][8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float4 x0 = *reinterpret_cast<const float4*>(&G[(8 * pa + i) * SLD + 8 * pc]);
-    const float4 x1 = *reinterpret_cast<const float4*>(&G[(8 * pa + i) * SLD + 8 * pc + 4]);
-    g[i][0] = x0.x; g[i][1] = x0.y; g[i][2] = x0.z; g[i][3] = x0.w;
-    g[i][4] = x1.x; g[i][5] = x1.y; g[i][6] = x1.z; g[i][7] = x1.w;
-  }
-  float d[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) d[i] = 1.f;
   auto bar_all = [] { asm volatile("bar.sync 2, %0;" ::"n"(TRI_THREADS) : "memory"); };
-  bar_all();                                                // every patch is in registers: G becomes the staging area
-  TT_MARK(tt, 0, tt_last);                                  // prologue
-
-#define TRI_STEP0(TYPE, S, BAR)                                                                             \
-  do {                                                                                                      \
-    if (is_param) tri_param_step_full<TYPE>(g, d, writes, csh + ((S) & (QRING - 1)) * 64, hist + (S) * 64, pa, (BAR)); \
-    else tri_bulk_step<TYPE>(g, csh + ((S) & (QRING - 1)) * 64, pa, pc, (BAR));                             \
-  } while (0)
-#define TRI_STEP(TYPE, S, BAR)                                                                              \
-  do {                                                                                                      \
-    if (is_param)                                                                                           \
-      tri_param_step<TYPE, (TYPE) == 3>(g, d, tid >> 4, csh + ((S) & (QRING - 1)) * 64, cring + ((S) & (QRING - 1)) * 16, hist + (S) * 64, pa, (BAR)); \
-    else tri_bulk_step<TYPE>(g, csh + ((S) & (QRING - 1)) * 64, pa, pc, (BAR));                             \
-  } while (0)
-  TRI_STEP0(0, 0, 8);
-  TRI_STEP0(1, 1, 9);
-  TRI_STEP0(2, 2, 10);
-  TT_MARK(tt, 1, tt_last);                                  // first three steps
+  // The two roles run their own copies of the sweep (same barriers in the same order): the parameter warp keeps a plain
+  // 8x8 patch and the scales, the off-diagonal warps keep their patch PACKED for fma.rn.f32x2 -- in one loop the
+  // register allocator would have to hold both forms for every thread.
+  if (is_param) {
+    float g[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 x0 = *reinterpret_cast<const float4*>(&G[(8 * pa + i) * SLD + 8 * pc]);
+      const float4 x1 = *reinterpret_cast<const float4*>(&G[(8 * pa + i) * SLD + 8 * pc + 4]);
+      g[i][0] = x0.x; g[i][1] = x0.y; g[i][2] = x0.z; g[i][3] = x0.w;
+      g[i][4] = x1.x; g[i][5] = x1.y; g[i][6] = x1.z; g[i][7] = x1.w;
+    }
+    float d[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = 1.f;
+    bar_all();                                              // every patch is in registers: G becomes the staging area
+    TT_MARK(tt, 0, tt_last);                                // prologue
+    tri_param_step_full<0>(g, d, writes, csh + 0 * 64, hist + 0 * 64, pa, 8);
+    tri_param_step_full<1>(g, d, writes, csh + 1 * 64, hist + 1 * 64, pa, 9);
+    tri_param_step_full<2>(g, d, writes, csh + 2 * 64, hist + 2 * 64, pa, 10);
+    TT_MARK(tt, 1, tt_last);                                // first three steps
+#define TRI_PSTEP(TYPE, S, BAR) \
+  tri_param_step<TYPE, (TYPE) == 3>(g, d, tid >> 4, csh + ((S) & (QRING - 1)) * 64, cring + ((S) & (QRING - 1)) * 16, hist + (S) * 64, pa, (BAR))
 #pragma unroll 1
-  for (int r = 0; r < QROUNDS; ++r) {
-    const int s0 = 3 + 4 * r;
-    // what this round's move will do to this patch: looked up BEFORE the steps, while the off-diagonal warps would
-    // otherwise sit at the first step's barrier (the lookups are off the critical path of the round's end)
-    const unsigned char* qs = qsrc + (r < QROUNDS - 1 ? r : 0) * 32;
-    const int rsrcL = qs[2 * pa], rsrcH = qs[2 * pa + 1], csrcL = qs[2 * pc], csrcH = qs[2 * pc + 1];
-    const bool mrL = rsrcL != 8 * pa, mrH = rsrcH != 8 * pa + 4, mcL = csrcL != 8 * pc, mcH = csrcH != 8 * pc + 4;
-    const bool mv[4] = {mrL || mcL, mrL || mcH, mrH || mcL, mrH || mcH};
-    TRI_STEP(3, s0 + 0, 4);
-    TRI_STEP(4, s0 + 1, 5);
-    TRI_STEP(5, s0 + 2, 6);
-    TRI_STEP(6, s0 + 3, 7);
-    TT_MARK(tt, 2, tt_last);                                // the parameter warp's four steps
-    if (r == QROUNDS - 1) break;
-    if ((r & 7) == 7) {
-      // fold the deferred scales back into the stored values; the replay kernel folds the same values into R
-      if (is_param) {
+    for (int r = 0; r < QROUNDS; ++r) {
+      const int s0 = 3 + 4 * r;
+      // what this round's move will do to this patch: looked up before the steps, off the critical path of the round's end
+      const unsigned char* qs = qsrc + (r < QROUNDS - 1 ? r : 0) * 32;
+      const int rsrcL = qs[2 * pa], rsrcH = qs[2 * pa + 1];
+      const bool mL = rsrcL != 8 * pa, mH = rsrcH != 8 * pa + 4;
+      const bool mv[4] = {mL, mL || mH, mH || mL, mH};
+      TRI_PSTEP(3, s0 + 0, 4);
+      TRI_PSTEP(4, s0 + 1, 5);
+      TRI_PSTEP(5, s0 + 2, 6);
+      TRI_PSTEP(6, s0 + 3, 7);
+      TT_MARK(tt, 2, tt_last);                              // the parameter warp's four steps
+      if (r == QROUNDS - 1) break;
+      if ((r & 7) == 7) {
+        // fold the deferred scales back into the stored values; the replay kernel folds the same values into R
         if (writes) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) { dfold[8 * pa + i] = d[i]; a_dhist[(r >> 3) * JK + 8 * pa + i] = d[i]; }
         }
+        bar_all();
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int jj = i; jj < 8; ++jj) g[i][jj] *= d[i] * d[jj];
 #pragma unroll
         for (int i = 0; i < 8; ++i) d[i] = 1.f;
       }
-      bar_all();
-      float dr[8], dc[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { dr[i] = dfold[8 * pa + i]; dc[i] = dfold[8 * pc + i]; }
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g[i][j] *= dr[i] * dc[j];
-      // (dfold is next written eight rounds later, behind many blocking barriers)
-    }
-    TT_MARK(tt, 3, tt_last);                                // fold
-    // ---- quad move through the staging area: only what changes place
-    if (writes) {
-      if (is_param) {
+      TT_MARK(tt, 3, tt_last);                              // fold
+      // ---- quad move through the staging area: only what changes place
+      if (writes) {
         quad_stage_write_diag(G, g, pa, mv);
 #pragma unroll
         for (int i = 0; i < 8; ++i) dmov[8 * pa + i] = d[i];
-      } else {
-        quad_stage_write(G, g, pa, pc, mv);
-        quad_stage_write_t(G, g, pa, pc, mv);
       }
-    }
-    TT_MARK(tt, 4, tt_last);                                // its staging writes
-    bar_all();
-    TT_MARK(tt, 5, tt_last);                                // waiting for the off-diagonal warps at the move barrier
-    // The parameter warp reads first: its new diagonal patches head the next round's chain, the off-diagonal warps have a
-    // whole step of slack before they need theirs (they follow on barrier 3 instead of crowding the shared-memory pipe)
-    if (is_param) {
-      quad_stage_read(G, g, rsrcL, rsrcH, csrcL, csrcH, mv);
+      TT_MARK(tt, 4, tt_last);                              // its staging writes
+      bar_all();
+      TT_MARK(tt, 5, tt_last);                              // waiting for the off-diagonal warps at the move barrier
+      // The parameter warp reads first: its new diagonal patches head the next round's chain, the off-diagonal warps have
+      // a whole step of slack before they need theirs (they follow on barrier 3 instead of crowding the shared-memory pipe)
+      quad_stage_read(G, g, rsrcL, rsrcH, rsrcL, rsrcH, mv);
 #pragma unroll
       for (int i = 0; i < 8; ++i) d[i] = dmov[(i < 4 ? rsrcL : rsrcH) + (i & 3)];
       asm volatile("" ::"f"(g[0][0]), "f"(g[0][7]), "f"(g[7][7]), "f"(d[0]), "f"(d[7]) : "memory");   // the loads have landed
       __syncwarp();
       asm volatile("bar.arrive 3, %0;" ::"n"(TRI_THREADS) : "memory");
-    } else {
-      asm volatile("bar.sync 3, %0;" ::"n"(TRI_THREADS) : "memory");
-      quad_stage_read(G, g, rsrcL, rsrcH, csrcL, csrcH, mv);
+      TT_MARK(tt, 6, tt_last);                              // its staging reads
+      // no second CTA barrier: the next write of the staging area (and of dmov) lies behind the next round's first step
+      // barrier, at which this warp WAITS and every off-diagonal thread arrives after its reads
     }
-    TT_MARK(tt, 6, tt_last);                                // its staging reads
-    // no second barrier: the next write of the staging area (and of dmov) lies behind the next round's first step
-    // barrier, at which the parameter warp WAITS and every off-diagonal thread arrives after these reads
-  }
-#undef TRI_STEP
-#undef TRI_STEP0
-  if (is_param && writes) {
+#undef TRI_PSTEP
+    if (writes) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { gd[8 * pa + i] = d[i] * d[i] * g[i][i]; a_dfin[8 * pa + i] = d[i]; }
+      for (int i = 0; i < 8; ++i) { gd[8 * pa + i] = d[i] * d[i] * g[i][i]; a_dfin[8 * pa + i] = d[i]; }
+    }
+  } else {
+    f32x2 gp[8][4];                                         // gp[i][c] = (G[8pa + i][8pc + 2c], G[8pa + i][8pc + 2c + 1])
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 x0 = *reinterpret_cast<const float4*>(&G[(8 * pa + i) * SLD + 8 * pc]);
+      const float4 x1 = *reinterpret_cast<const float4*>(&G[(8 * pa + i) * SLD + 8 * pc + 4]);
+      gp[i][0] = pk2(x0.x, x0.y); gp[i][1] = pk2(x0.z, x0.w); gp[i][2] = pk2(x1.x, x1.y); gp[i][3] = pk2(x1.z, x1.w);
+    }
+    bar_all();                                              // every patch is in registers: G becomes the staging area
+    {
+      float g[8][8];                                        // the three steps inside the quads pair differently: plain form
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) upk2(gp[i][c], g[i][2 * c], g[i][2 * c + 1]);
+      tri_bulk_step<0>(g, csh + 0 * 64, pa, pc, 8);
+      tri_bulk_step<1>(g, csh + 1 * 64, pa, pc, 9);
+      tri_bulk_step<2>(g, csh + 2 * 64, pa, pc, 10);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) gp[i][c] = pk2(g[i][2 * c], g[i][2 * c + 1]);
+    }
+#define TRI_BSTEP(TYPE, S, BAR) tri_bulk_step_packed<TYPE>(gp, csh + ((S) & (QRING - 1)) * 64, pa, pc, (BAR))
+#pragma unroll 1
+    for (int r = 0; r < QROUNDS; ++r) {
+      const int s0 = 3 + 4 * r;
+      const unsigned char* qs = qsrc + (r < QROUNDS - 1 ? r : 0) * 32;
+      const int rsrcL = qs[2 * pa], rsrcH = qs[2 * pa + 1], csrcL = qs[2 * pc], csrcH = qs[2 * pc + 1];
+      const bool mrL = rsrcL != 8 * pa, mrH = rsrcH != 8 * pa + 4, mcL = csrcL != 8 * pc, mcH = csrcH != 8 * pc + 4;
+      const bool mv[4] = {mrL || mcL, mrL || mcH, mrH || mcL, mrH || mcH};
+      TRI_BSTEP(3, s0 + 0, 4);
+      TRI_BSTEP(4, s0 + 1, 5);
+      TRI_BSTEP(5, s0 + 2, 6);
+      TRI_BSTEP(6, s0 + 3, 7);
+      if (r == QROUNDS - 1) break;
+      if ((r & 7) == 7) {
+        bar_all();
+        float dr[8], dc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { dr[i] = dfold[8 * pa + i]; dc[i] = dfold[8 * pc + i]; }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float a, bb; upk2(gp[i][c], a, bb);
+            gp[i][c] = pk2(a * (dr[i] * dc[2 * c]), bb * (dr[i] * dc[2 * c + 1]));
+          }
+        // (dfold is next written eight rounds later, behind many blocking barriers)
+      }
+      float g[8][8];                                        // plain view for the staging helpers (register pairs renamed)
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) upk2(gp[i][c], g[i][2 * c], g[i][2 * c + 1]);
+      if (writes) {
+        quad_stage_write(G, g, pa, pc, mv);
+        quad_stage_write_t(G, g, pa, pc, mv);
+      }
+      bar_all();
+      asm volatile("bar.sync 3, %0;" ::"n"(TRI_THREADS) : "memory");   // after the parameter warp's reads
+      quad_stage_read(G, g, rsrcL, rsrcH, csrcL, csrcH, mv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) gp[i][c] = pk2(g[i][2 * c], g[i][2 * c + 1]);
+    }
+#undef TRI_BSTEP
   }
   bar_all();
   if (tid < JK) {
     const float dd = gd[tid];
     int rank = 0;
-    for (int j = 0; j < JK; ++j) {
-      const float e = gd[j];
-      rank += (e > dd) || (e == dd && j < tid);
+    for (int jj = 0; jj < JK; ++jj) {
+      const float e = gd[jj];
+      rank += (e > dd) || (e == dd && jj < tid);
     }
     a_dest[tid] = rank;
   }
@@ -376,15 +476,6 @@ constexpr int RCHUNK = 16;                                  // steps per bulk co
 constexpr int RCHUNKS = (QSTEPS + RCHUNK - 1) / RCHUNK;
 constexpr size_t SOLVETR_SMEM = sizeof(float) * (JK * SLD) + sizeof(float) * JK * (QFOLDS + 1) + sizeof(int) * JK + (QROUNDS - 1) * 32;
 static_assert(sizeof(float2) * QSTEPS * 64 <= sizeof(float) * JK * SLD, "the record must fit the sorted-R buffer");
-
-// Packed FP32 pairs (fma.rn.f32x2): measured on this part (scripts/probes/ffma2_replay_probe.cu) the replay's inner loop
-// takes 325 clocks per step with scalar FFMA and 163 with FFMA2 -- the packed instruction issues at the scalar rate.
-// The patch is held TRANSPOSED, rp[j][k] = (R[2k][j], R[2k+1][j]): a column rotation touches whole columns, so both
-// halves of a pair see the same multiplier.  Each half is the fma.rn the scalar code performs: results are bitwise equal.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 
 template <int TYPE>
 __device__ __forceinline__ void tri_r_step(f32x2 (&rp)[8][4], const float2* hist, int step, int pc, uint64_t* mb) {
