@@ -11,12 +11,16 @@
 //     (parameters -> publish -> rotate its own patch, no loads, no barrier waits) ahead of everybody else;
 //   * G is symmetric: patch (c, a) is the transpose of (a, c).  120 threads hold one patch of every unordered pair
 //     of groups; a patch gets row rotations of its row group and column rotations of its column group as before.
-// So a CTA is 5 warps: warp 0 = the 16 diagonal lanes (parameter chain), warps 1-4 = 120 off-diagonal patches.
-// 160 threads x <= 128 registers and 73 KB of shared memory: THREE pairs per SM, whose chains interleave.
-// A quad move stages the full matrix as before: off-diagonal threads write their moving sub-blocks in both
-// orientations (the transpose is a different register selection, not a shuffle), every thread reads what its slot
-// receives.  The diagonal lanes keep full 8x8 patches (both triangles, rotated independently), so after a move an
-// element may descend from either copy: they agree to rounding, and the kernel is deterministic.
+// So a CTA is 5 warps: warp 0 = the diagonal patches (parameter chain; lane g computes pivots 0-1 of group g, lane g + 16
+// pivots 2-3, both keep bit-identical copies of the patch), warps 1-4 = 120 off-diagonal patches, held packed for
+// fma.rn.f32x2 during the four steps of a round.  The two roles run their own copies of the sweep (same barriers in the
+// same order), so neither carries the other's registers.  160 threads x 128 registers and 76 KB of shared memory:
+// THREE pairs per SM, whose chains interleave.
+// A quad move stages the full matrix: off-diagonal threads write their moving sub-blocks in both orientations (the
+// transpose is a different register selection, not a shuffle), every thread reads what its slot receives.  The diagonal
+// lanes keep the UPPER triangle of their patches only (symmetric cell update, 76 FMAs instead of 128) and stage the
+// lower one from its mirror image; after a move an element of an off-diagonal patch may descend from either orientation
+// of its source: the two agree to rounding, and the kernel is deterministic.
 constexpr int TRI_THREADS = 160;
 #ifdef ASVD_SOLVE_TIMING
 // timing build (scripts/tri_timing.py): clock64 marks of lane 0 of CTA (0,0); [0..7] G kernel, [8..15] replay kernel
@@ -283,9 +287,9 @@ solve_tri_g_kernel(const float* __restrict__ Gpart, int chunks, int pairs_per_ma
   float* a_dfin = a_dhist + QFOLDS * JK;                    // [JK]
   int* a_dest = reinterpret_cast<int*>(a_dfin + JK);        // [JK]
 
-  // Roles.  Warp 0: lanes 0-15 hold the diagonal patches (lanes 16-31 shadow them: same instructions, nothing
-  // published).  Warps 1-4: thread lt = tid - 32 holds patch (a, a + delta) of the unordered pair {a, a + delta},
-  // delta = 1..7 for every a (112 threads), delta = 8 for a < 8 (8 threads); the last 8 threads shadow patch (0, 8).
+  // Roles.  Warp 0: lanes g and g + 16 hold the diagonal patch of group g (each computes two of its four pivots; lanes
+  // 0-15 do the staging and record writes).  Warps 1-4: thread lt = tid - 32 holds patch (a, a + delta) of the unordered pair {a, a + delta},
+  // delta = 1..7 for every a (112 threads), delta = 8 for a < 8 (8 threads); the last 8 threads shadow the delta = 8 patches (same work, no writes).
   // Eight consecutive lanes differ in a AND in c modulo 8: staging accesses in either orientation hit distinct banks.
   const bool is_param = tid < 32;
   int pa, pc;
