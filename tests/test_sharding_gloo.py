@@ -26,6 +26,12 @@ def test_lpt_partition_balances_llama_shapes():
         loads = [sum(costs[n] for n in s) for s in shards]
         assert max(loads) / (sum(loads) / world) < 1.02            # SURVEY: 1.001 / 1.005 / 1.009
     assert lpt_partition(costs, 4) == lpt_partition(costs, 4)      # deterministic
+    # the cost follows the measured times: a pre-conditioned 2.7:1 rectangle is 1.5-1.8 squares, not
+    # 2.7; the 7.8:1 lm_head (direct path, alone in its batch) several
+    sq = layer_cost(4096, 4096)
+    assert 1.4 < layer_cost(11008, 4096) / sq < 2.0 and layer_cost(11008, 4096) == layer_cost(4096, 11008)
+    assert 5.0 < layer_cost(32000, 4096) / sq < 10.0
+    assert layer_cost(768, 3072) > layer_cost(768, 768)
 
 
 def _worker(rank, world, port, q):
