@@ -1,6 +1,6 @@
 // Tensor-core (tcgen05, kind::tf32) bodies of the two streaming passes of the block-Jacobi SVD.
 //
-// fp32 accuracy on a TF32 pipe: every fp32 operand x is split as x = hi + lo with hi = rna_tf32(x) (exactly
+// fp32 accuracy on a TF32 pipe: every fp32 operand x is split as x = hi + lo with hi = x rounded or truncated to tf32 (exactly
 // representable, so the MMA's internal truncation is a no-op) and lo = x - hi (|lo| <= 2^-11 |x|); a product is
 // accumulated as hi*hi + lo*hi + hi*lo in the fp32 TMEM accumulator, dropping only the 2^-22 lo*lo term.  The
 // split is done in shared memory by dedicated warps between the TMA landing and the MMA issue.
@@ -12,7 +12,7 @@
 //   warp 2  TMEM allocator
 //   warps 4-7  epilogue: tcgen05.ld -> global partial Gram
 //   warps 8-15 split (precise mode, two groups of four taking the tiles in turn): thread t owns row t of the landed tile;
-//              hi = rna_tf32(x) goes back in place, the
+//              hi = x with the low mantissa bits cleared (the raw tile stays as it is), the
 //              A operand (0.5 hi | lo) goes to TENSOR MEMORY (tcgen05.st)
 // Precise mode computes only T = (0.5 HI + LO) HI^T -- two MMAs per K-step, A from tensor memory, B = the hi tile
 // in shared memory -- and the solve kernel forms G = T + T^T = HI HI^T + LO HI^T + HI LO^T.  Against three
@@ -40,18 +40,20 @@ __device__ __forceinline__ float rna_tf32(float x) {
   return __uint_as_float(r);
 }
 
-// hi/lo split of a 16 KB tile by 128 threads (layout-agnostic: same offsets in both tiles); hi is rewritten in
-// place with its tf32-rounded value.  All loads are issued before the first store.
-__device__ __forceinline__ void split_tile(float4* hi, float4* lo, int t) {
+// hi/lo split of a 16 KB tile by 128 threads (layout-agnostic: same offsets in both tiles).  hi = x with the 13 low
+// mantissa bits cleared -- what the tensor core makes of the RAW tile when it reads it as a kind::tf32 operand --, so the
+// landed tile is left as it is and only lo = x - hi (exact) is written: a quarter less shared-memory traffic in the
+// split than rounding hi and writing it back in place (what this function did until round 2's second session), and no
+// generic-proxy write to a tile the epilogue later overwrites.  All loads are issued before the first store.
+__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+__device__ __forceinline__ void split_tile(const float4* hi, float4* lo, int t) {
   float4 v[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = hi[t + 128 * j];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float4 h = make_float4(rna_tf32(v[j].x), rna_tf32(v[j].y), rna_tf32(v[j].z), rna_tf32(v[j].w));
-    hi[t + 128 * j] = h;
-    lo[t + 128 * j] = make_float4(v[j].x - h.x, v[j].y - h.y, v[j].z - h.z, v[j].w - h.w);
-  }
+  for (int j = 0; j < 8; ++j)
+    lo[t + 128 * j] = make_float4(v[j].x - trunc_tf32(v[j].x), v[j].y - trunc_tf32(v[j].y), v[j].z - trunc_tf32(v[j].z),
+                                  v[j].w - trunc_tf32(v[j].w));
 }
 
 // One launch serves the matrices whose mode precise_b[b] equals `precise` (the mode is a per-matrix state, so that a
